@@ -1,0 +1,595 @@
+// C ABI of include/enterp.h: handle management, one-time upload of the resolved tables, kernel
+// dispatch, and the host-buffer pipelines. No CPU evaluation path exists in this file or anywhere
+// in the library: every eval entry point ends in a kernel launch or an error status.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/enterp.h"
+#include "launch.hpp"
+#include "resolve.hpp"
+
+namespace enterp {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+  static std::mutex mu;
+  static std::vector<int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)cache.size() <= dev) cache.resize(dev + 1, 0);
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+static thread_local std::string t_cuda_error;
+static enterp_status cuda_fail(cudaError_t e, const char* where) {
+  t_cuda_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  cudaGetLastError();  // clear sticky-less errors
+  return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice ? ENTERP_NO_DEVICE
+                                                                                                    : ENTERP_CUDA_ERROR;
+}
+#define CK(call, where)                                  \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Scratch of the host-buffer pipelines (double buffered), cached per replica.
+struct HostPipe {
+  void* dev_in[2] = {nullptr, nullptr};
+  void* dev_out[2] = {nullptr, nullptr};
+  void* stage_in[2] = {nullptr, nullptr};
+  void* stage_out[2] = {nullptr, nullptr};
+  size_t dev_in_bytes = 0, dev_out_bytes = 0, stage_in_bytes = 0, stage_out_bytes = 0;
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  std::mutex mu;
+};
+
+struct Replica {
+  int device = -1;
+  void* store = nullptr;
+  void* elems = nullptr;
+  void* lvl[MAX_LEVELS] = {};
+  int n_lvl = 0;
+  unsigned long long* invalid = nullptr;
+  HostPipe pipe;
+};
+
+}  // namespace enterp
+
+using namespace enterp;
+
+struct enterp_curve {
+  Resolved r;
+  std::mutex mu;
+  std::vector<Replica*> replicas;  // index = device ordinal
+};
+
+namespace {
+
+size_t rsize(const Resolved& r) { return r.scalar == ENTERP_F32 ? 4 : 8; }
+
+enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
+  if (device < 0) return ENTERP_NO_DEVICE;
+  int n = 0;
+  CK(cudaGetDeviceCount(&n), "cudaGetDeviceCount");
+  if (device >= n) return ENTERP_NO_DEVICE;
+  if ((int)c->replicas.size() <= device) c->replicas.resize(device + 1, nullptr);
+  if (c->replicas[device]) {
+    *out = c->replicas[device];
+    return ENTERP_OK;
+  }
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  Replica* rp = new Replica();
+  rp->device = device;
+  auto put = [&](const std::vector<unsigned char>& host, void** dev) -> cudaError_t {
+    *dev = nullptr;
+    if (host.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc(dev, host.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dev, host.data(), host.size(), cudaMemcpyHostToDevice);
+  };
+  cudaError_t e = put(c->r.store, &rp->store);
+  if (e == cudaSuccess) e = put(c->r.elems, &rp->elems);
+  rp->n_lvl = (int)c->r.levels.level.size();
+  for (int l = 0; l < rp->n_lvl && e == cudaSuccess; ++l) e = put(c->r.levels.level[l], &rp->lvl[l]);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&rp->invalid, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(rp->invalid, 0, sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    cudaFree(rp->store);
+    cudaFree(rp->elems);
+    for (int l = 0; l < MAX_LEVELS; ++l) cudaFree(rp->lvl[l]);
+    cudaFree(rp->invalid);
+    delete rp;
+    return cuda_fail(e, "curve upload");
+  }
+  c->replicas[device] = rp;
+  *out = rp;
+  return ENTERP_OK;
+}
+
+enterp_status get_replica(enterp_curve* c, int device, Replica** out) {
+  std::lock_guard<std::mutex> lk(c->mu);
+  return upload_locked(c, device, out);
+}
+
+template <class R>
+CurveDev<R> make_dev(const Resolved& r, const Replica& rp) {
+  CurveDev<R> d{};
+  const R* store = static_cast<const R*>(rp.store);
+  d.vk = store ? store + r.vk_off : nullptr;
+  d.ik = store ? store + r.ik_off : nullptr;
+  d.elems = static_cast<const R*>(rp.elems);
+  d.n_lvl = rp.n_lvl;
+  for (int l = 0; l < MAX_LEVELS; ++l) d.lvl[l] = static_cast<const R*>(rp.lvl[l]);
+  d.n_elem = (uint32_t)r.n_elem;
+  d.inner_len = (uint32_t)r.inner_len;
+  d.virt_len = (uint32_t)r.virt_len;
+  d.degree = (uint32_t)r.degree;
+  d.imin = (uint32_t)r.imin;
+  d.imax = (uint32_t)r.imax;
+  d.map0 = (uint32_t)r.map0;
+  d.mapL = (uint32_t)r.mapL;
+  d.map_add = (int32_t)r.map_add;
+  d.eq_step = (R)r.eq_step;
+  d.eq_offset = (R)r.eq_offset;
+  d.eq_first = (R)r.eq_first;
+  d.eq_lenm2 = r.inner_len >= 2 ? (R)(r.inner_len - 2) : R(0);  // from_usize(len - 2), list.rs:546
+  d.in_add = (R)r.in_add;
+  d.in_mul = (R)r.in_mul;
+  d.has_transform = r.has_transform;
+  d.invalid = rp.invalid;
+  return d;
+}
+
+// Stepper::new(n_total, start, end) -> Equidistant::new (list.rs:393-399): step in R arithmetic.
+template <class R>
+SampleSrc<R> take_src(const Resolved& r, uint64_t n_total, uint64_t first, uint64_t count) {
+  SampleSrc<R> s{};
+  const R start = (R)r.domain[0], end = (R)r.domain[1];
+  const R span = end - start;
+  const R denom = (R)(n_total - 1);
+  s.t = nullptr;
+  s.step = span / denom;
+  s.start = start;
+  s.first = first;
+  s.count = count;
+  return s;
+}
+template <class R>
+SampleSrc<R> batch_src(const void* t, uint64_t n) {
+  SampleSrc<R> s{};
+  s.t = static_cast<const R*>(t);
+  s.step = R(0);
+  s.start = R(0);
+  s.first = 0;
+  s.count = n;
+  return s;
+}
+
+template <class R>
+enterp_status dispatch_eval(const Resolved& r, const Replica& rp, const SampleSrc<R>& s, void* out, cudaStream_t st) {
+  const CurveDev<R> d = make_dev<R>(r, rp);
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 16u) == 0;
+  const bool proj = r.weighted != 0;
+  const bool equi = r.knot_base == ENTERP_KNOTS_EQUIDISTANT;
+  cudaError_t e;
+  switch (r.kind) {
+    case ENTERP_BSPLINE: {
+      if (r.degree > (uint64_t)MAX_DYN_DEGREE) return ENTERP_UNSUPPORTED;
+      const int deg = r.degree <= 7 ? (int)r.degree : 0;
+      e = launch_bspline<R>(r.dh, proj, deg, equi, d, s, static_cast<R*>(out), vec_ok, st);
+      break;
+    }
+    case ENTERP_LINEAR:
+      e = launch_linear<R>(r.dh, proj, equi, d, s, static_cast<R*>(out), vec_ok, st);
+      break;
+    default: {
+      if (r.n_elem > (uint64_t)MAX_DYN_BEZIER) return ENTERP_UNSUPPORTED;
+      const int n = r.n_elem <= 16 ? (int)r.n_elem : 0;
+      e = launch_bezier<R>(r.dh, proj, n, d, s, static_cast<R*>(out), vec_ok, st);
+      break;
+    }
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  return ENTERP_OK;
+}
+
+enterp_status eval_common(enterp_curve* c, int device, bool take, const void* t, uint64_t n_total, uint64_t first,
+                          uint64_t count, void* out, void* stream) {
+  if (!c) return ENTERP_INVALID_ARGUMENT;
+  if (count == 0) return ENTERP_OK;
+  if (!out || (!take && !t)) return ENTERP_INVALID_ARGUMENT;
+  if (take && (n_total == 0 || first + count > n_total)) return ENTERP_INVALID_ARGUMENT;
+  Replica* rp = nullptr;
+  enterp_status st = get_replica(c, device, &rp);
+  if (st) return st;
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (c->r.scalar == ENTERP_F32) {
+    auto s = take ? take_src<float>(c->r, n_total, first, count) : batch_src<float>(t, count);
+    return dispatch_eval<float>(c->r, *rp, s, out, cs);
+  }
+  auto s = take ? take_src<double>(c->r, n_total, first, count) : batch_src<double>(t, count);
+  return dispatch_eval<double>(c->r, *rp, s, out, cs);
+}
+
+enterp_status span_common(enterp_curve* c, int device, bool take, const void* t, uint64_t n_total, uint64_t first,
+                          uint64_t count, uint32_t* idx, void* factor, void* stream) {
+  if (!c) return ENTERP_INVALID_ARGUMENT;
+  if (count == 0) return ENTERP_OK;
+  if (!idx || (!take && !t)) return ENTERP_INVALID_ARGUMENT;
+  if (take && (n_total == 0 || first + count > n_total)) return ENTERP_INVALID_ARGUMENT;
+  Replica* rp = nullptr;
+  enterp_status st = get_replica(c, device, &rp);
+  if (st) return st;
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  const bool equi = c->r.knot_base == ENTERP_KNOTS_EQUIDISTANT;
+  cudaError_t e;
+  if (c->r.scalar == ENTERP_F32) {
+    auto s = take ? take_src<float>(c->r, n_total, first, count) : batch_src<float>(t, count);
+    e = launch_span<float>(c->r.kind, equi, make_dev<float>(c->r, *rp), s, idx, static_cast<float*>(factor), cs);
+  } else {
+    auto s = take ? take_src<double>(c->r, n_total, first, count) : batch_src<double>(t, count);
+    e = launch_span<double>(c->r.kind, equi, make_dev<double>(c->r, *rp), s, idx, static_cast<double*>(factor), cs);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "span kernel launch");
+  return ENTERP_OK;
+}
+
+// ---- host-buffer pipelines ---------------------------------------------------------------------
+constexpr uint64_t HOST_CHUNK = 1ull << 22;  // samples per pipeline stage
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+cudaError_t ensure(void** p, size_t* have, size_t need, bool host) {
+  if (*have >= need) return cudaSuccess;
+  if (*p) {
+    if (host) cudaFreeHost(*p); else cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+  }
+  cudaError_t e = host ? cudaMallocHost(p, need) : cudaMalloc(p, need);
+  if (e == cudaSuccess) *have = need;
+  return e;
+}
+
+enterp_status host_common(enterp_curve* c, int device, bool take, const void* t_host, uint64_t n_total, uint64_t first,
+                          uint64_t count, void* out_host) {
+  if (!c) return ENTERP_INVALID_ARGUMENT;
+  if (count == 0) return ENTERP_OK;
+  if (!out_host || (!take && !t_host)) return ENTERP_INVALID_ARGUMENT;
+  if (take && (n_total == 0 || first + count > n_total)) return ENTERP_INVALID_ARGUMENT;
+  Replica* rp = nullptr;
+  enterp_status st = get_replica(c, device, &rp);
+  if (st) return st;
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  HostPipe& hp = rp->pipe;
+  std::lock_guard<std::mutex> lk(hp.mu);
+  const size_t rs = rsize(c->r);
+  const size_t out_stride = rs * c->r.dim;
+  const uint64_t chunk = count < HOST_CHUNK ? count : HOST_CHUNK;
+  const bool pin_in = take || is_pinned(t_host);
+  const bool pin_out = is_pinned(out_host);
+  for (int b = 0; b < 2; ++b) {
+    if (!hp.stream[b]) CK(cudaStreamCreateWithFlags(&hp.stream[b], cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!hp.done[b]) CK(cudaEventCreateWithFlags(&hp.done[b], cudaEventDisableTiming), "cudaEventCreate");
+  }
+  {
+    size_t a = hp.dev_in_bytes, b = hp.dev_in_bytes;
+    if (!take) {
+      CK(ensure(&hp.dev_in[0], &a, chunk * rs, false), "cudaMalloc");
+      CK(ensure(&hp.dev_in[1], &b, chunk * rs, false), "cudaMalloc");
+      hp.dev_in_bytes = a < b ? a : b;
+    }
+    a = b = hp.dev_out_bytes;
+    CK(ensure(&hp.dev_out[0], &a, chunk * out_stride, false), "cudaMalloc");
+    CK(ensure(&hp.dev_out[1], &b, chunk * out_stride, false), "cudaMalloc");
+    hp.dev_out_bytes = a < b ? a : b;
+    if (!pin_in) {
+      a = b = hp.stage_in_bytes;
+      CK(ensure(&hp.stage_in[0], &a, chunk * rs, true), "cudaMallocHost");
+      CK(ensure(&hp.stage_in[1], &b, chunk * rs, true), "cudaMallocHost");
+      hp.stage_in_bytes = a < b ? a : b;
+    }
+    if (!pin_out) {
+      a = b = hp.stage_out_bytes;
+      CK(ensure(&hp.stage_out[0], &a, chunk * out_stride, true), "cudaMallocHost");
+      CK(ensure(&hp.stage_out[1], &b, chunk * out_stride, true), "cudaMallocHost");
+      hp.stage_out_bytes = a < b ? a : b;
+    }
+  }
+  struct Pending {
+    bool live = false;
+    uint64_t off = 0, n = 0;
+  } pend[2];
+  auto retire = [&](int b) -> cudaError_t {
+    if (!pend[b].live) return cudaSuccess;
+    cudaError_t e = cudaEventSynchronize(hp.done[b]);
+    if (e != cudaSuccess) return e;
+    if (!pin_out)
+      std::memcpy(static_cast<char*>(out_host) + pend[b].off * out_stride, hp.stage_out[b], pend[b].n * out_stride);
+    pend[b].live = false;
+    return cudaSuccess;
+  };
+  uint64_t k = 0;
+  for (uint64_t off = 0; off < count; off += chunk, ++k) {
+    const int b = (int)(k & 1);
+    const uint64_t n = count - off < chunk ? count - off : chunk;
+    CK(retire(b), "pipeline wait");
+    const void* t_dev = nullptr;
+    if (!take) {
+      const char* src = static_cast<const char*>(t_host) + off * rs;
+      if (!pin_in) {
+        std::memcpy(hp.stage_in[b], src, n * rs);
+        src = static_cast<const char*>(hp.stage_in[b]);
+      }
+      CK(cudaMemcpyAsync(hp.dev_in[b], src, n * rs, cudaMemcpyHostToDevice, hp.stream[b]), "H2D");
+      t_dev = hp.dev_in[b];
+    }
+    enterp_status es;
+    if (c->r.scalar == ENTERP_F32) {
+      auto s = take ? take_src<float>(c->r, n_total, first + off, n) : batch_src<float>(t_dev, n);
+      es = dispatch_eval<float>(c->r, *rp, s, hp.dev_out[b], hp.stream[b]);
+    } else {
+      auto s = take ? take_src<double>(c->r, n_total, first + off, n) : batch_src<double>(t_dev, n);
+      es = dispatch_eval<double>(c->r, *rp, s, hp.dev_out[b], hp.stream[b]);
+    }
+    if (es) return es;
+    void* dst = pin_out ? static_cast<void*>(static_cast<char*>(out_host) + off * out_stride) : hp.stage_out[b];
+    CK(cudaMemcpyAsync(dst, hp.dev_out[b], n * out_stride, cudaMemcpyDeviceToHost, hp.stream[b]), "D2H");
+    CK(cudaEventRecord(hp.done[b], hp.stream[b]), "cudaEventRecord");
+    pend[b].live = true;
+    pend[b].off = off;
+    pend[b].n = n;
+  }
+  CK(retire(0), "pipeline drain");
+  CK(retire(1), "pipeline drain");
+  return ENTERP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+ENTERP_API enterp_status enterp_curve_validate(const enterp_curve_desc* desc, int stage, enterp_error_info* err) {
+  if (!desc) return ENTERP_INVALID_ARGUMENT;
+  return validate(*desc, stage, err);
+}
+
+ENTERP_API enterp_status enterp_curve_create(const enterp_curve_desc* desc, enterp_curve** out, enterp_error_info* err) {
+  if (out) *out = nullptr;
+  if (!desc || !out) return ENTERP_INVALID_ARGUMENT;
+  enterp_curve* c = new enterp_curve();
+  enterp_status st = resolve(*desc, c->r, err);
+  if (st) {
+    delete c;
+    return st;
+  }
+  *out = c;
+  return ENTERP_OK;
+}
+
+ENTERP_API void enterp_curve_destroy(enterp_curve* c) {
+  if (!c) return;
+  for (Replica* rp : c->replicas) {
+    if (!rp) continue;
+    DeviceGuard g(rp->device);
+    cudaFree(rp->store);
+    cudaFree(rp->elems);
+    for (int l = 0; l < MAX_LEVELS; ++l) cudaFree(rp->lvl[l]);
+    cudaFree(rp->invalid);
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(rp->pipe.dev_in[b]);
+      cudaFree(rp->pipe.dev_out[b]);
+      if (rp->pipe.stage_in[b]) cudaFreeHost(rp->pipe.stage_in[b]);
+      if (rp->pipe.stage_out[b]) cudaFreeHost(rp->pipe.stage_out[b]);
+      if (rp->pipe.stream[b]) cudaStreamDestroy(rp->pipe.stream[b]);
+      if (rp->pipe.done[b]) cudaEventDestroy(rp->pipe.done[b]);
+    }
+    delete rp;
+  }
+  delete c;
+}
+
+ENTERP_API enterp_status enterp_curve_get_info(const enterp_curve* c, enterp_curve_info* info) {
+  if (!c || !info) return ENTERP_INVALID_ARGUMENT;
+  const Resolved& r = c->r;
+  info->kind = r.kind;
+  info->scalar = r.scalar;
+  info->dim = r.dim;
+  info->weighted = r.weighted;
+  info->knot_base = r.knot_base;
+  info->adaptor = r.adaptor;
+  info->n_elements = r.n_elem;
+  info->n_knots = r.virt_len;
+  info->degree = r.degree;
+  info->border = r.border_n;
+  info->domain[0] = r.domain[0];
+  info->domain[1] = r.domain[1];
+  return ENTERP_OK;
+}
+
+ENTERP_API enterp_status enterp_curve_domain(const enterp_curve* c, double out[2]) {
+  if (!c || !out) return ENTERP_INVALID_ARGUMENT;
+  out[0] = c->r.domain[0];
+  out[1] = c->r.domain[1];
+  return ENTERP_OK;
+}
+
+ENTERP_API enterp_status enterp_curve_upload(enterp_curve* c, int device) {
+  if (!c) return ENTERP_INVALID_ARGUMENT;
+  Replica* rp = nullptr;
+  return get_replica(c, device, &rp);
+}
+
+ENTERP_API enterp_status enterp_eval_batch(enterp_curve* c, int device, const void* t_dev, uint64_t n, void* out_dev,
+                                           void* stream) {
+  return eval_common(c, device, false, t_dev, 0, 0, n, out_dev, stream);
+}
+
+ENTERP_API enterp_status enterp_eval_take(enterp_curve* c, int device, uint64_t n_total, uint64_t first, uint64_t count,
+                                          void* out_dev, void* stream) {
+  return eval_common(c, device, true, nullptr, n_total, first, count, out_dev, stream);
+}
+
+ENTERP_API enterp_status enterp_span_batch(enterp_curve* c, int device, const void* t_dev, uint64_t n, uint32_t* idx_dev,
+                                           void* factor_dev, void* stream) {
+  return span_common(c, device, false, t_dev, 0, 0, n, idx_dev, factor_dev, stream);
+}
+
+ENTERP_API enterp_status enterp_span_take(enterp_curve* c, int device, uint64_t n_total, uint64_t first, uint64_t count,
+                                          uint32_t* idx_dev, void* factor_dev, void* stream) {
+  return span_common(c, device, true, nullptr, n_total, first, count, idx_dev, factor_dev, stream);
+}
+
+ENTERP_API enterp_status enterp_stepper(int scalar, int device, double start, double end, uint64_t n_total,
+                                        uint64_t first, uint64_t count, void* t_out_dev, void* stream) {
+  if (count == 0) return ENTERP_OK;
+  if (!t_out_dev || n_total == 0 || first + count > n_total) return ENTERP_INVALID_ARGUMENT;
+  if (scalar != ENTERP_F32 && scalar != ENTERP_F64) return ENTERP_INVALID_ARGUMENT;
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  Resolved r;
+  r.domain[0] = start;
+  r.domain[1] = end;
+  cudaError_t e;
+  if (scalar == ENTERP_F32)
+    e = launch_stepper<float>(take_src<float>(r, n_total, first, count), static_cast<float*>(t_out_dev),
+                              static_cast<cudaStream_t>(stream));
+  else
+    e = launch_stepper<double>(take_src<double>(r, n_total, first, count), static_cast<double*>(t_out_dev),
+                               static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "stepper launch");
+  return ENTERP_OK;
+}
+
+ENTERP_API enterp_status enterp_bezier_many_take(int scalar, int dim, uint64_t n_curves, uint32_t n_ctrl,
+                                                 const void* ctrl_dev, uint32_t samples_per_curve, int device,
+                                                 void* out_dev, void* stream) {
+  if (n_curves == 0 || samples_per_curve == 0) return ENTERP_OK;
+  if (!ctrl_dev || !out_dev || dim < 1 || dim > 4) return ENTERP_INVALID_ARGUMENT;
+  if (scalar != ENTERP_F32 && scalar != ENTERP_F64) return ENTERP_INVALID_ARGUMENT;
+  if (n_ctrl < 1) return ENTERP_EMPTY;  // bezier/builder.rs:141
+  if (n_ctrl > (uint32_t)MAX_DYN_BEZIER) return ENTERP_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  const int n = n_ctrl <= 16 ? (int)n_ctrl : 0;
+  cudaError_t e;
+  if (scalar == ENTERP_F32) {
+    const float step = (1.0f - 0.0f) / (float)(uint64_t)(samples_per_curve - 1);
+    e = launch_bezier_many<float>(dim, n, static_cast<const float*>(ctrl_dev), n_curves, n_ctrl, samples_per_curve, step,
+                                  static_cast<float*>(out_dev), static_cast<cudaStream_t>(stream));
+  } else {
+    const double step = (1.0 - 0.0) / (double)(uint64_t)(samples_per_curve - 1);
+    e = launch_bezier_many<double>(dim, n, static_cast<const double*>(ctrl_dev), n_curves, n_ctrl, samples_per_curve,
+                                   step, static_cast<double*>(out_dev), static_cast<cudaStream_t>(stream));
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "bezier_many launch");
+  return ENTERP_OK;
+}
+
+ENTERP_API enterp_status enterp_sample_host(enterp_curve* c, int device, const void* t_host, uint64_t n, void* out_host) {
+  return host_common(c, device, false, t_host, 0, 0, n, out_host);
+}
+
+ENTERP_API enterp_status enterp_take_host(enterp_curve* c, int device, uint64_t n_total, uint64_t first, uint64_t count,
+                                          void* out_host) {
+  return host_common(c, device, true, nullptr, n_total, first, count, out_host);
+}
+
+ENTERP_API enterp_status enterp_host_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr) return ENTERP_INVALID_ARGUMENT;
+  *ptr = nullptr;
+  CK(cudaMallocHost(ptr, bytes), "cudaMallocHost");
+  return ENTERP_OK;
+}
+
+ENTERP_API void enterp_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+ENTERP_API enterp_status enterp_invalid_count(enterp_curve* c, int device, unsigned long long* n) {
+  if (!c || !n) return ENTERP_INVALID_ARGUMENT;
+  Replica* rp = nullptr;
+  enterp_status st = get_replica(c, device, &rp);
+  if (st) return st;
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  CK(cudaMemcpy(n, rp->invalid, sizeof(unsigned long long), cudaMemcpyDeviceToHost), "cudaMemcpy");
+  return ENTERP_OK;
+}
+
+ENTERP_API const char* enterp_status_str(enterp_status s) {
+  switch (s) {
+    case ENTERP_OK: return "ok";
+    case ENTERP_TOO_FEW_ELEMENTS: return "TooFewElements";
+    case ENTERP_TOO_FEW_KNOTS: return "TooFewKnots";
+    case ENTERP_KNOT_ELEMENT_INEQUALITY: return "KnotElementInequality";
+    case ENTERP_NOT_SORTED: return "NotSorted";
+    case ENTERP_INCONGRUOUS_ELEMENTS_KNOTS: return "IncongruousElementsKnots";
+    case ENTERP_INCONGRUOUS_ELEMENTS_DEGREE: return "IncongruousElementsDegree";
+    case ENTERP_INVALID_DEGREE: return "InvalidDegree";
+    case ENTERP_TOO_SMALL_WORKSPACE: return "TooSmallWorkspace";
+    case ENTERP_EMPTY: return "Empty";
+    case ENTERP_INVALID_ARGUMENT: return "invalid argument";
+    case ENTERP_UNSUPPORTED: return "unsupported";
+    case ENTERP_NO_DEVICE: return "no CUDA device";
+    case ENTERP_CUDA_ERROR: return "CUDA error";
+  }
+  return "unknown status";
+}
+
+ENTERP_API const char* enterp_last_cuda_error(void) { return t_cuda_error.c_str(); }
+
+ENTERP_API int enterp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+ENTERP_API unsigned long long enterp_launch_count(void) { return g_launches.load(); }
+
+ENTERP_API const char* enterp_version(void) { return "enterpolation_b200 0.1.0 (sm_100a; reference enterpolation 0.3.0)"; }
+
+}  // extern "C"

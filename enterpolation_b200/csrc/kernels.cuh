@@ -1,0 +1,425 @@
+// Hand-written sm_100a kernels of the curve-evaluation hot path.
+//
+// Arithmetic contract: every floating-point operation the reference performs is performed here
+// with the same operands, in the same order, with IEEE round-to-nearest and NO contraction
+// (intrinsics __f*_rn / __d*_rn are never fused by nvcc/ptxas). Table lookups replace the
+// reference's recomputation of knots (resolve.cpp builds the tables with the same operations),
+// and `1 - factor` is hoisted once per merge because all components share it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace enterp {
+
+constexpr int MAX_LEVELS = 7;     // 32^7 > 2^31 searched knots
+constexpr int MAX_DYN_DEGREE = 63;  // runtime-degree de Boor keeps its workspace in local memory
+constexpr int MAX_DYN_BEZIER = 256;
+constexpr int BLOCK = 256;
+
+template <class R>
+struct CurveDev {
+  const R* vk;     // virtual knot vector (BorderBuffer / BorderDeletion already applied)
+  const R* ik;     // innermost knot chain (what the search runs on)
+  const R* elems;  // [n_elem][DH], homogeneous-lifted when weighted
+  const R* lvl[MAX_LEVELS];  // 32-ary pivot pyramid, top level first, NaN padded
+  int n_lvl;
+  uint32_t n_elem, inner_len, virt_len, degree;
+  uint32_t imin, imax, map0, mapL;
+  int32_t map_add;
+  R eq_step, eq_offset, eq_first, eq_lenm2;
+  R in_add, in_mul;
+  int has_transform;
+  unsigned long long* invalid;  // device counter: samples where the reference would panic
+};
+
+template <class R>
+struct SampleSrc {
+  const R* t;                // batch mode: parameters; take mode: nullptr
+  R step, start;             // take mode: t_i = step * fl(i) + start (list.rs:416-418)
+  unsigned long long first;  // take mode: global index of this launch's sample 0
+  unsigned long long count;  // samples in this launch
+};
+
+// ---- exact arithmetic -------------------------------------------------------------------------
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float from_index(unsigned long long i, float) { return __ull2float_rn(i); }
+__device__ __forceinline__ double from_index(unsigned long long i, double) { return __ull2double_rn(i); }
+__device__ __forceinline__ float qnan(float) { return __int_as_float(0x7fc00000); }
+__device__ __forceinline__ double qnan(double) { return __longlong_as_double(0x7ff8000000000000ll); }
+
+// Merge::merge (topology-traits 0.1.2 blanket impl == utils.rs:6-12): a*(1-f) + b*f.
+template <class R>
+__device__ __forceinline__ R merge1(R a, R b, R f, R omf) {
+  return xadd(xmul(a, omf), xmul(b, f));
+}
+
+// ---- sample parameter --------------------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ R sample_param(const SampleSrc<R>& s, unsigned long long i) {
+  if (s.t) return __ldcs(s.t + i);
+  return xadd(xmul(s.step, from_index(s.first + i, R(0))), s.start);
+}
+
+// ---- span search -------------------------------------------------------------------------------
+// `floor(scaled).to_usize().unwrap()` (list.rs:456, 486): valid iff 0 <= scaled < 2^64.
+template <class R>
+__device__ __forceinline__ bool to_usize_ok(R v) {
+  return (v >= R(0)) && (v < R(18446744073709551616.0));
+}
+
+// Equidistant::strict_upper_bound_clamped (list.rs:476-488) on the inner chain.
+template <class R>
+__device__ __forceinline__ bool equi_inner_index(const CurveDev<R>& c, R x, uint32_t& idx) {
+  if (x < c.eq_first) {
+    idx = c.imin;
+    return true;
+  }
+  const R scaled = xdiv(xsub(x, c.eq_offset), c.eq_step);
+  if (!to_usize_ok(scaled)) return false;
+  const R fl = floor(scaled);
+  if (fl >= R(4294967040.0)) {
+    idx = c.imax;
+  } else {
+    const uint32_t u = (uint32_t)fl;
+    idx = u >= c.imax ? c.imax : u + 1u;
+  }
+  return true;
+}
+
+// Warp-cooperative 32-ary search: number of knots of ik[imin, imax) that are <= x, for each lane's
+// own x. Equals the reference's branchy binary search (list.rs:69-86) on sorted knots, including
+// ties (x == knot goes up), repeated knots and NaN (-> 0). All 32 lanes must call.
+template <class R>
+__device__ __forceinline__ uint32_t coop_count_le(const CurveDev<R>& c, R x) {
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t mine = 0;
+#pragma unroll 4
+  for (int s = 0; s < 32; ++s) {
+    const R xs = __shfl_sync(0xffffffffu, x, s);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int l = 0; l < MAX_LEVELS; ++l) {
+      if (l < c.n_lvl) {
+        const R v = __ldg(c.lvl[l] + ((size_t)cnt * 32u + lane));
+        cnt = cnt * 32u + __popc(__ballot_sync(0xffffffffu, v <= xs));
+      }
+    }
+    if (lane == (unsigned)s) mine = cnt;
+  }
+  return mine;
+}
+
+// inner index -> virtual index: BorderBuffer::map_from (adaptors.rs:31-39) / BorderDeletion (-1).
+template <class R>
+__device__ __forceinline__ uint32_t map_from_inner(const CurveDev<R>& c, uint32_t inner_idx) {
+  if (inner_idx == c.inner_len) return c.mapL;
+  if (inner_idx == 0) return c.map0;
+  return (uint32_t)((int32_t)inner_idx + c.map_add);
+}
+
+// BSpline span: knots.strict_upper_bound_clamped(x, degree, len - degree) (bspline/mod.rs:148-154).
+template <class R, bool EQUI>
+__device__ __forceinline__ bool bspline_span(const CurveDev<R>& c, R x, uint32_t& index) {
+  uint32_t inner;
+  bool ok = true;
+  if (EQUI) {
+    ok = equi_inner_index(c, x, inner);
+    if (!ok) inner = c.imin;
+  } else {
+    inner = c.imin + coop_count_le(c, x);
+  }
+  index = map_from_inner(c, inner);
+  return ok;
+}
+
+// Linear span: knots.upper_border(x) -> (min, max, factor) (list.rs:169-248 / 532-551).
+template <class R, bool EQUI>
+__device__ __forceinline__ bool linear_border(const CurveDev<R>& c, R x, uint32_t& imin, uint32_t& imax, R& factor) {
+  const uint32_t len = c.inner_len;
+  if (EQUI) {
+    const R scaled = xdiv(xsub(x, c.eq_offset), c.eq_step);
+    if (x < c.eq_offset) {
+      imin = 0;
+      imax = 1;
+      factor = scaled;
+      return true;
+    }
+    const R cl = ceil(scaled);
+    if (!to_usize_ok(scaled) || !(cl < R(18446744073709551616.0))) {
+      imin = 0;
+      imax = 1;
+      factor = qnan(R(0));
+      return false;
+    }
+    const R fl = floor(scaled);
+    const bool beyond = cl >= R(4294967040.0) || (uint32_t)cl >= len;
+    if (beyond) {
+      imin = len - 2;
+      imax = len - 1;
+      factor = xsub(scaled, c.eq_lenm2);
+    } else {
+      imin = (uint32_t)fl;
+      imax = (uint32_t)cl;
+      factor = xsub(scaled, trunc(scaled));  // Real::fract
+    }
+    return true;
+  } else {
+    const uint32_t m = coop_count_le(c, x);  // strict_upper_bound over the whole chain
+    const bool edge = (m == len) || (m == 0);
+    imax = m == len ? len - 1 : (m == 0 ? 1u : m);
+    imin = imax - 1;
+    const R kmin = __ldg(c.ik + imin), kmax = __ldg(c.ik + imax);
+    const R div = xsub(kmax, kmin);
+    // linear_factor (checked, 232-248) on the edges, linear_factor_unchecked (212-224) inside
+    factor = (edge && div == R(0)) ? div : xdiv(xsub(x, kmin), div);
+    return true;
+  }
+}
+
+// ---- output stores -----------------------------------------------------------------------------
+template <class R, int D>
+__device__ __forceinline__ void store_elem(R* __restrict__ out, unsigned long long i, const R (&v)[D], bool vec_ok) {
+  R* p = out + i * D;
+  constexpr int BYTES = D * (int)sizeof(R);
+  if (BYTES % 16 == 0 && vec_ok) {
+    constexpr int N4 = BYTES / 16;
+    const float4* src = reinterpret_cast<const float4*>(v);
+#pragma unroll
+    for (int k = 0; k < N4; ++k) __stcs(reinterpret_cast<float4*>(p) + k, src[k]);
+  } else if (BYTES % 8 == 0 && vec_ok) {
+    constexpr int N2 = BYTES / 8;
+    const float2* src = reinterpret_cast<const float2*>(v);
+#pragma unroll
+    for (int k = 0; k < N2; ++k) __stcs(reinterpret_cast<float2*>(p) + k, src[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) __stcs(p + k, v[k]);
+  }
+}
+
+template <class R, int DH, bool PROJ>
+__device__ __forceinline__ void finish_and_store(R* __restrict__ out, unsigned long long i, const R* w0, bool valid,
+                                                 bool vec_ok, unsigned long long* invalid) {
+  constexpr int D = PROJ ? DH - 1 : DH;
+  R v[D];
+  if (PROJ) {
+    // Homogeneous::project (weights/homogeneous.rs:134-136): element / rational, true divisions
+    const R rat = w0[DH - 1];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = xdiv(w0[k], rat);
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = w0[k];
+  }
+  if (!valid) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = qnan(R(0));
+    atomicAdd(invalid, 1ull);
+  }
+  store_elem<R, D>(out, i, v, vec_ok);
+}
+
+// =================================================================================================
+// BSpline: span -> gather degree+1 elements and 2*degree knots -> de Boor (bspline/mod.rs:145-169)
+// DEG == 0: runtime degree (DynSpace semantics; workspace in local memory).
+// =================================================================================================
+template <class R, int DH, bool PROJ, int DEG, bool EQUI>
+__global__ void __launch_bounds__(BLOCK) bspline_kernel(const CurveDev<R> c, const SampleSrc<R> s, R* __restrict__ out,
+                                                        const bool vec_ok) {
+  constexpr int P_CAP = DEG > 0 ? DEG : MAX_DYN_DEGREE;
+  const int p = DEG > 0 ? DEG : (int)c.degree;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * BLOCK; base < s.count;
+       base += (unsigned long long)gridDim.x * BLOCK) {
+    const unsigned long long i = base + threadIdx.x;
+    const bool active = i < s.count;
+    R x = active ? sample_param(s, i) : c.eq_first;
+    uint32_t index;
+    bool valid = bspline_span<R, EQUI>(c, x, index);
+    if (!active) continue;
+    const uint32_t first = index - (uint32_t)p;
+    R kn[2 * P_CAP];
+    R ws[(P_CAP + 1) * DH];
+    const R* __restrict__ vk = c.vk + first;
+    const R* __restrict__ el = c.elems + (size_t)first * DH;
+    if (DEG > 0) {
+#pragma unroll
+      for (int m = 0; m < 2 * P_CAP; ++m) kn[m] = __ldg(vk + m);
+#pragma unroll
+      for (int m = 0; m < (P_CAP + 1) * DH; ++m) ws[m] = __ldg(el + m);
+#pragma unroll
+      for (int r = 1; r <= P_CAP; ++r) {
+#pragma unroll
+        for (int j = 0; j <= P_CAP - r; ++j) {
+          // i = j + r + index - p ; knots[i-1] = kn[j+r-1] ; knots[i+p-r] = kn[p+j]
+          const R left = kn[j + r - 1];
+          const R f = xdiv(xsub(x, left), xsub(kn[P_CAP + j], left));
+          const R omf = xsub(R(1), f);
+#pragma unroll
+          for (int k = 0; k < DH; ++k) ws[j * DH + k] = merge1(ws[j * DH + k], ws[(j + 1) * DH + k], f, omf);
+        }
+      }
+    } else {
+      for (int m = 0; m < 2 * p; ++m) kn[m] = __ldg(vk + m);
+      for (int m = 0; m < (p + 1) * DH; ++m) ws[m] = __ldg(el + m);
+      for (int r = 1; r <= p; ++r) {
+        for (int j = 0; j <= p - r; ++j) {
+          const R left = kn[j + r - 1];
+          const R f = xdiv(xsub(x, left), xsub(kn[p + j], left));
+          const R omf = xsub(R(1), f);
+#pragma unroll
+          for (int k = 0; k < DH; ++k) ws[j * DH + k] = merge1(ws[j * DH + k], ws[(j + 1) * DH + k], f, omf);
+        }
+      }
+    }
+    finish_and_store<R, DH, PROJ>(out, i, ws, valid, vec_ok, c.invalid);
+  }
+}
+
+// =================================================================================================
+// Linear: upper_border -> two element fetches -> merge (linear/mod.rs:122-128), Identity easing.
+// =================================================================================================
+template <class R, int DH, bool PROJ, bool EQUI>
+__global__ void __launch_bounds__(BLOCK) linear_kernel(const CurveDev<R> c, const SampleSrc<R> s, R* __restrict__ out,
+                                                       const bool vec_ok) {
+  for (unsigned long long base = (unsigned long long)blockIdx.x * BLOCK; base < s.count;
+       base += (unsigned long long)gridDim.x * BLOCK) {
+    const unsigned long long i = base + threadIdx.x;
+    const bool active = i < s.count;
+    R x = active ? sample_param(s, i) : R(0);
+    uint32_t imin, imax;
+    R f;
+    const bool valid = linear_border<R, EQUI>(c, x, imin, imax, f);
+    if (!active) continue;
+    const R omf = xsub(R(1), f);
+    R w[DH];
+    const R* __restrict__ a = c.elems + (size_t)imin * DH;
+    const R* __restrict__ b = c.elems + (size_t)imax * DH;
+#pragma unroll
+    for (int k = 0; k < DH; ++k) w[k] = merge1(__ldg(a + k), __ldg(b + k), f, omf);
+    finish_and_store<R, DH, PROJ>(out, i, w, valid, vec_ok, c.invalid);
+  }
+}
+
+// =================================================================================================
+// Bezier (one curve): copy all elements -> de Casteljau triangle (bezier/mod.rs:44-56, 78-91, 240-246)
+// N == 0: runtime element count (workspace in local memory).
+// =================================================================================================
+template <class R, int DH, bool PROJ, int N>
+__global__ void __launch_bounds__(BLOCK) bezier_kernel(const CurveDev<R> c, const SampleSrc<R> s, R* __restrict__ out,
+                                                       const bool vec_ok) {
+  constexpr int N_CAP = N > 0 ? N : MAX_DYN_BEZIER;
+  const int n = N > 0 ? N : (int)c.n_elem;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; i < s.count;
+       i += (unsigned long long)gridDim.x * BLOCK) {
+    R x = sample_param(s, i);
+    if (c.has_transform) x = xadd(xmul(x, c.in_mul), c.in_add);  // TransformInput::eval (adaptors.rs:141-152)
+    const R omx = xsub(R(1), x);
+    R ws[N_CAP * DH];
+    if (N > 0) {
+#pragma unroll
+      for (int m = 0; m < N_CAP * DH; ++m) ws[m] = __ldg(c.elems + m);
+#pragma unroll
+      for (int k = 1; k <= N_CAP - 1; ++k)
+#pragma unroll
+        for (int j = 0; j < N_CAP - k; ++j)
+#pragma unroll
+          for (int q = 0; q < DH; ++q) ws[j * DH + q] = merge1(ws[j * DH + q], ws[(j + 1) * DH + q], x, omx);
+    } else {
+      for (int m = 0; m < n * DH; ++m) ws[m] = __ldg(c.elems + m);
+      for (int k = 1; k <= n - 1; ++k)
+        for (int j = 0; j < n - k; ++j)
+#pragma unroll
+          for (int q = 0; q < DH; ++q) ws[j * DH + q] = merge1(ws[j * DH + q], ws[(j + 1) * DH + q], x, omx);
+    }
+    finish_and_store<R, DH, PROJ>(out, i, ws, true, vec_ok, c.invalid);
+  }
+}
+
+// =================================================================================================
+// Many Bezier curves x take(samples) on [0,1]: one warp per curve, lanes stride the samples.
+// ctrl [n_curves][N][D] -> out [n_curves][samples][D].
+// =================================================================================================
+template <class R, int D, int N>
+__global__ void __launch_bounds__(BLOCK) bezier_many_kernel(const R* __restrict__ ctrl, unsigned long long n_curves,
+                                                            uint32_t n_ctrl, uint32_t samples, R step,
+                                                            R* __restrict__ out) {
+  constexpr int N_CAP = N > 0 ? N : MAX_DYN_BEZIER;
+  const int n = N > 0 ? N : (int)n_ctrl;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long warps = ((unsigned long long)gridDim.x * BLOCK) >> 5;
+  for (unsigned long long curve = (((unsigned long long)blockIdx.x * BLOCK + threadIdx.x) >> 5); curve < n_curves;
+       curve += warps) {
+    const R* __restrict__ cp = ctrl + curve * (unsigned long long)n * D;
+    for (uint32_t sidx = lane; sidx < samples; sidx += 32u) {
+      const R x = xadd(xmul(step, from_index(sidx, R(0))), R(0));  // Stepper over [0,1]
+      const R omx = xsub(R(1), x);
+      R ws[N_CAP * D];
+      if (N > 0) {
+#pragma unroll
+        for (int m = 0; m < N_CAP * D; ++m) ws[m] = __ldg(cp + m);
+#pragma unroll
+        for (int k = 1; k <= N_CAP - 1; ++k)
+#pragma unroll
+          for (int j = 0; j < N_CAP - k; ++j)
+#pragma unroll
+            for (int q = 0; q < D; ++q) ws[j * D + q] = merge1(ws[j * D + q], ws[(j + 1) * D + q], x, omx);
+      } else {
+        for (int m = 0; m < n * D; ++m) ws[m] = __ldg(cp + m);
+        for (int k = 1; k <= n - 1; ++k)
+          for (int j = 0; j < n - k; ++j)
+#pragma unroll
+            for (int q = 0; q < D; ++q) ws[j * D + q] = merge1(ws[j * D + q], ws[(j + 1) * D + q], x, omx);
+      }
+      R* p = out + (curve * samples + sidx) * D;
+#pragma unroll
+      for (int q = 0; q < D; ++q) __stcs(p + q, ws[q]);
+    }
+  }
+}
+
+// =================================================================================================
+// Parity / debug kernels: span decision only, and the stepper values.
+// kind: 0 linear, 1 bezier, 2 bspline
+// =================================================================================================
+template <class R, int KIND, bool EQUI>
+__global__ void __launch_bounds__(BLOCK) span_kernel(const CurveDev<R> c, const SampleSrc<R> s, uint32_t* __restrict__ idx,
+                                                     R* __restrict__ factor) {
+  for (unsigned long long base = (unsigned long long)blockIdx.x * BLOCK; base < s.count;
+       base += (unsigned long long)gridDim.x * BLOCK) {
+    const unsigned long long i = base + threadIdx.x;
+    const bool active = i < s.count;
+    R x = active ? sample_param(s, i) : R(0);
+    uint32_t index = 0;
+    R f = R(0);
+    bool valid = true;
+    if (KIND == 2) {
+      valid = bspline_span<R, EQUI>(c, x, index);
+    } else if (KIND == 0) {
+      uint32_t lo;
+      valid = linear_border<R, EQUI>(c, x, lo, index, f);
+    }
+    if (!active) continue;
+    if (!valid) {
+      index = 0xFFFFFFFFu;
+      f = qnan(R(0));
+    }
+    idx[i] = index;
+    if (factor) factor[i] = f;
+  }
+}
+
+template <class R>
+__global__ void __launch_bounds__(BLOCK) stepper_kernel(const SampleSrc<R> s, R* __restrict__ out) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; i < s.count;
+       i += (unsigned long long)gridDim.x * BLOCK)
+    out[i] = sample_param(s, i);
+}
+
+}  // namespace enterp

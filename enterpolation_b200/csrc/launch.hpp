@@ -1,0 +1,49 @@
+// Host-callable launchers for the kernel families in kernels.cuh. Each family is instantiated in
+// its own translation unit (inst_*.cu) so that nvcc can compile them in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace enterp {
+
+// Total kernels launched by this library in this process (enterp_launch_count()).
+void count_launch();
+// SM count of the current device (cached per device).
+int sm_count();
+
+// Grid for a grid-stride kernel: enough CTAs to fill every SM at the kernel's own occupancy, never
+// more than the work needs. `kernel` is the __global__ function pointer.
+template <class K>
+int grid_for(K kernel, unsigned long long work_items, int items_per_block) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  unsigned long long want = (work_items + items_per_block - 1) / items_per_block;
+  unsigned long long cap = (unsigned long long)per_sm * (unsigned long long)sm_count();
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+// dh: components in the recursion (dim + weighted); proj: weighted -> divide by the last component.
+// deg: 1..7 compile-time degree, 0 = runtime degree (<= MAX_DYN_DEGREE).
+template <class R>
+cudaError_t launch_bspline(int dh, bool proj, int deg, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
+                           bool vec_ok, cudaStream_t st);
+template <class R>
+cudaError_t launch_linear(int dh, bool proj, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
+                          cudaStream_t st);
+// n: 1..16 compile-time element count, 0 = runtime (<= MAX_DYN_BEZIER)
+template <class R>
+cudaError_t launch_bezier(int dh, bool proj, int n, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
+                          cudaStream_t st);
+template <class R>
+cudaError_t launch_bezier_many(int dim, int n, const R* ctrl, unsigned long long n_curves, uint32_t n_ctrl,
+                               uint32_t samples, R step, R* out, cudaStream_t st);
+template <class R>
+cudaError_t launch_span(int kind, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, uint32_t* idx, R* factor,
+                        cudaStream_t st);
+template <class R>
+cudaError_t launch_stepper(const SampleSrc<R>& s, R* out, cudaStream_t st);
+
+}  // namespace enterp

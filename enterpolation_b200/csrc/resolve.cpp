@@ -1,0 +1,420 @@
+// See resolve.hpp. Compiled with -ffp-contract=off: table entries must carry exactly the bits the
+// reference's per-access arithmetic would produce.
+#include "resolve.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace enterp {
+namespace {
+
+struct Fail {
+  enterp_status status;
+  uint64_t found, necessary, index;
+  int32_t mode;
+};
+inline Fail ok() { return {ENTERP_OK, 0, 0, 0, 0}; }
+inline Fail fail(enterp_status s, uint64_t found = 0, uint64_t necessary = 0, int32_t mode = 0, uint64_t index = 0) {
+  return {s, found, necessary, index, mode};
+}
+
+// Sorted::new — src/base/list.rs:263-278: error index = first i whose predecessor is greater or
+// unordered (NaN).
+template <class R>
+Fail sorted_check(const void* knots, uint64_t n) {
+  const R* k = static_cast<const R*>(knots);
+  for (uint64_t i = 1; i < n; ++i) {
+    const R a = k[i - 1], b = k[i];
+    const bool ordered = (a < b) || (a == b);
+    if (!ordered) return fail(ENTERP_NOT_SORTED, 0, 0, 0, i);
+  }
+  return ok();
+}
+Fail sorted_check(const enterp_curve_desc& d) {
+  if (d.n_knots && !d.knots) return fail(ENTERP_INVALID_ARGUMENT);
+  return d.scalar == ENTERP_F32 ? sorted_check<float>(d.knots, d.n_knots) : sorted_check<double>(d.knots, d.n_knots);
+}
+
+// The shape a chain resolves to (filled progressively, stage by stage).
+struct Shape {
+  int32_t adaptor = AD_NONE;
+  uint64_t border_n = 0, inner_len = 0, virt_len = 0, degree = 0, space_len = 0;
+};
+
+// ---- stage 0: .elements(..) / .elements_with_weights(..) ---------------------------------------
+Fail check_elements(const enterp_curve_desc& d) {
+  if (d.kind != ENTERP_LINEAR && d.kind != ENTERP_BEZIER && d.kind != ENTERP_BSPLINE) return fail(ENTERP_INVALID_ARGUMENT);
+  if (d.scalar != ENTERP_F32 && d.scalar != ENTERP_F64) return fail(ENTERP_INVALID_ARGUMENT);
+  if (d.dim < 1 || d.dim > 4) return fail(ENTERP_INVALID_ARGUMENT);
+  if (d.n_elements && !d.elements) return fail(ENTERP_INVALID_ARGUMENT);
+  if (d.weighted && d.n_elements && !d.weights) return fail(ENTERP_INVALID_ARGUMENT);
+  if (d.n_elements >= (1ull << 31)) return fail(ENTERP_UNSUPPORTED);
+  if (d.kind == ENTERP_BEZIER) {
+    // src/bezier/builder.rs:141, 178
+    return d.n_elements < 1 ? fail(ENTERP_EMPTY) : ok();
+  }
+  // src/linear/builder.rs:172, 230; src/bspline/builder.rs:232, 269
+  return d.n_elements < 2 ? fail(ENTERP_TOO_FEW_ELEMENTS, d.n_elements) : ok();
+}
+
+// ---- stage 1: knots --------------------------------------------------------------------------
+Fail check_knots(const enterp_curve_desc& d, Shape& s) {
+  const uint64_t e = d.n_elements, k = d.n_knots, c = d.eq_count;
+  if (d.kind == ENTERP_BEZIER) {
+    s.degree = e - 1;
+    return ok();
+  }
+  if (d.knot_base != ENTERP_KNOTS_SORTED && d.knot_base != ENTERP_KNOTS_EQUIDISTANT) return fail(ENTERP_INVALID_ARGUMENT);
+  if (d.knot_base == ENTERP_KNOTS_SORTED && k >= (1ull << 31)) return fail(ENTERP_UNSUPPORTED);
+  if (d.kind == ENTERP_LINEAR) {
+    s.degree = 1;
+    if (d.knot_base == ENTERP_KNOTS_SORTED) {
+      // src/linear/builder.rs:331 (count) then 335 (Sorted::new)
+      if (k != e) return fail(ENTERP_KNOT_ELEMENT_INEQUALITY, e, k);
+      Fail f = sorted_check(d);
+      if (f.status) return f;
+      s.inner_len = s.virt_len = k;
+    } else {
+      // src/linear/builder.rs:427-453: as many equidistant knots as elements
+      if (d.eq_form < ENTERP_EQ_DOMAIN || d.eq_form > ENTERP_EQ_DISTANCE) return fail(ENTERP_INVALID_ARGUMENT);
+      s.inner_len = s.virt_len = e;
+    }
+    return ok();
+  }
+  // BSpline
+  if (d.mode < ENTERP_OPEN || d.mode > ENTERP_LEGACY) return fail(ENTERP_INVALID_ARGUMENT);
+  if (d.knot_base == ENTERP_KNOTS_SORTED) {
+    switch (d.mode) {
+      case ENTERP_OPEN:  // src/bspline/builder.rs:377-401
+        if (k < 2) return fail(ENTERP_TOO_FEW_KNOTS, k);
+        if (k < e || e <= k - e + 1) return fail(ENTERP_INCONGRUOUS_ELEMENTS_KNOTS, e, k, ENTERP_OPEN);
+        break;
+      case ENTERP_CLAMPED:  // 447-466
+        if (k < 2) return fail(ENTERP_TOO_FEW_KNOTS, k);
+        if (e < k) return fail(ENTERP_INCONGRUOUS_ELEMENTS_KNOTS, e, k, ENTERP_CLAMPED);
+        break;
+      default:  // ENTERP_LEGACY 512-534
+        if (k < 4) return fail(ENTERP_TOO_FEW_KNOTS, k);
+        if (k <= e + 1 || e < k - e) return fail(ENTERP_INCONGRUOUS_ELEMENTS_KNOTS, e, k, ENTERP_LEGACY);
+        break;
+    }
+    // Open/Clamped: `Sorted::new(knots)?`; Legacy unwraps (builder.rs:529, a panic upstream) —
+    // surfaced as NotSorted through the ABI instead of aborting the process.
+    Fail f = sorted_check(d);
+    if (f.status) return f;
+    s.inner_len = k;
+    if (d.mode == ENTERP_OPEN) {
+      s.adaptor = AD_NONE;
+      s.virt_len = k;
+    } else if (d.mode == ENTERP_CLAMPED) {
+      s.adaptor = AD_BORDER_BUFFER;
+      s.border_n = e - k;  // builder.rs:459
+      s.virt_len = k + 2 * s.border_n;
+    } else {
+      s.adaptor = AD_BORDER_DELETION;
+      s.virt_len = k - 2;
+    }
+  } else {
+    if (d.mode == ENTERP_LEGACY) return fail(ENTERP_UNSUPPORTED);  // no impl block upstream
+    if (d.eq_by != ENTERP_EQ_BY_DEGREE && d.eq_by != ENTERP_EQ_BY_QUANTITY) return fail(ENTERP_INVALID_ARGUMENT);
+    if (d.eq_form < ENTERP_EQ_DOMAIN || d.eq_form > ENTERP_EQ_DISTANCE) return fail(ENTERP_INVALID_ARGUMENT);
+    if (c >= (1ull << 31)) return fail(ENTERP_UNSUPPORTED);
+    const bool open = d.mode == ENTERP_OPEN;
+    uint64_t deg = 0;
+    if (d.eq_by == ENTERP_EQ_BY_DEGREE) {
+      // Open 633-655 / Clamped 780-798
+      if (c < 1) return fail(ENTERP_INVALID_DEGREE, c);
+      if (e <= c) return fail(ENTERP_INCONGRUOUS_ELEMENTS_DEGREE, e, c, d.mode);
+      deg = c;
+      s.inner_len = open ? e - 1 + c : e - c + 1;
+    } else {
+      // Open 673-692 (line 680 reports a *legacy*-flavoured error) / Clamped 820-836
+      if (c < 2) return fail(ENTERP_TOO_FEW_KNOTS, c);
+      if (open) {
+        if (c < e) return fail(ENTERP_INCONGRUOUS_ELEMENTS_KNOTS, e, c, ENTERP_LEGACY);
+        if (e <= c - e + 1) return fail(ENTERP_INCONGRUOUS_ELEMENTS_KNOTS, e, c, ENTERP_OPEN);
+        deg = c - e + 1;
+      } else {
+        if (e < c) return fail(ENTERP_INCONGRUOUS_ELEMENTS_KNOTS, e, c, ENTERP_CLAMPED);
+        deg = e - c + 1;
+      }
+      s.inner_len = c;
+    }
+    if (open) {  // 903-933
+      s.adaptor = AD_NONE;
+      s.virt_len = s.inner_len;
+    } else {  // 972-1017: BorderBuffer::new(Equidistant, deg - 1)
+      s.adaptor = AD_BORDER_BUFFER;
+      s.border_n = deg - 1;
+      s.virt_len = s.inner_len + 2 * s.border_n;
+    }
+  }
+  s.degree = s.virt_len - e + 1;  // src/bspline/mod.rs:254
+  return ok();
+}
+
+// ---- stage 2: workspace ------------------------------------------------------------------------
+Fail check_space(const enterp_curve_desc& d, Shape& s) {
+  const uint64_t e = d.n_elements;
+  if (d.kind == ENTERP_LINEAR) return ok();
+  if (d.space < ENTERP_SPACE_CONSTANT || d.space > ENTERP_SPACE_WORKSPACE) return fail(ENTERP_INVALID_ARGUMENT);
+  if (d.kind == ENTERP_BEZIER) {
+    if (d.input_form != ENTERP_INPUT_NORMALIZED && d.input_form != ENTERP_INPUT_DOMAIN) return fail(ENTERP_INVALID_ARGUMENT);
+    if (d.space == ENTERP_SPACE_WORKSPACE) {
+      // src/bezier/builder.rs:354-367 — the error is built with swapped arguments (line 359)
+      if (d.workspace_n < e) return fail(ENTERP_TOO_SMALL_WORKSPACE, e, d.workspace_n);
+      s.space_len = d.workspace_n;
+    } else {
+      s.space_len = e;  // dynamic 317-324; constant::<N>() pins N == len by type (330-340)
+    }
+    return ok();
+  }
+  const uint64_t deg = s.virt_len - e + 1;
+  if (d.space == ENTERP_SPACE_DYNAMIC) {
+    s.space_len = deg + 1;  // src/bspline/builder.rs:1071-1078
+    return ok();
+  }
+  // constant::<N>() 1087-1103, workspace(S) 1114-1130
+  if (d.workspace_n <= deg) return fail(ENTERP_TOO_SMALL_WORKSPACE, d.workspace_n, deg);
+  s.space_len = d.workspace_n;
+  return ok();
+}
+
+Fail run_stages(const enterp_curve_desc& d, int stage, Shape& s) {
+  Fail f = check_elements(d);
+  if (f.status || stage <= STAGE_ELEMENTS) return f;
+  f = check_knots(d, s);
+  if (f.status || stage <= STAGE_KNOTS) return f;
+  return check_space(d, s);
+}
+
+void report(const Fail& f, enterp_error_info* err) {
+  if (!err) return;
+  err->status = f.status;
+  err->mode = f.mode;
+  err->found = f.found;
+  err->necessary = f.necessary;
+  err->index = f.index;
+}
+
+// ---- table construction ------------------------------------------------------------------------
+template <class R>
+bool is_pow2(R v) {
+  if (!(v > R(0)) || !std::isfinite(v)) return false;
+  int ex;
+  return std::frexp(v, &ex) == R(0.5);
+}
+
+template <class R>
+void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
+  const R nan = std::numeric_limits<R>::quiet_NaN();
+  const uint64_t e = d.n_elements;
+  // elements -> [e][dh]; the (T, w) -> Homogeneous lift is one multiply per component with the
+  // same operands at every fetch (src/weights/mod.rs:38-40, homogeneous.rs:83-88, 119-124), so
+  // doing it once here is bit-identical. w == 0 keeps the raw element ("direction").
+  {
+    const R* el = static_cast<const R*>(d.elements);
+    const R* w = static_cast<const R*>(d.weights);
+    r.elems.resize(e * r.dh * sizeof(R));
+    R* out = reinterpret_cast<R*>(r.elems.data());
+    for (uint64_t i = 0; i < e; ++i) {
+      if (d.weighted) {
+        const R wi = w[i];
+        for (int c = 0; c < d.dim; ++c) out[i * r.dh + c] = (wi == R(0)) ? el[i * d.dim + c] : el[i * d.dim + c] * wi;
+        out[i * r.dh + d.dim] = wi;
+      } else {
+        for (int c = 0; c < d.dim; ++c) out[i * r.dh + c] = el[i * d.dim + c];
+      }
+    }
+  }
+  if (d.kind == ENTERP_BEZIER) {
+    r.domain[0] = 0.0;
+    r.domain[1] = 1.0;
+    if (d.input_form == ENTERP_INPUT_DOMAIN) {
+      // TransformInput::normalized_to_domain (src/base/adaptors.rs:137-139) and its domain()
+      // (161-166): note t -> t * 1/(end-start) + (-start), only "right" for start == 0.
+      const R start = (R)d.in_a, end = (R)d.in_b;
+      const R add = -start;
+      const R mul = R(1) / (end - start);
+      r.has_transform = 1;
+      r.in_add = add;
+      r.in_mul = mul;
+      r.domain[0] = (R)((R(0) - add) / mul);
+      r.domain[1] = (R)((R(1) - add) / mul);
+    }
+    return;
+  }
+  // inner knot chain values
+  std::vector<R> inner(s.inner_len);
+  if (d.knot_base == ENTERP_KNOTS_SORTED) {
+    std::memcpy(inner.data(), d.knots, s.inner_len * sizeof(R));
+  } else {
+    // Equidistant::{new, normalized, step} (src/base/list.rs:380-408) and eval (416-418):
+    // step * fl(i) + offset — two roundings per knot, exactly as recomputed upstream.
+    R step, offset;
+    const R len1 = (R)(s.inner_len - 1);
+    if (d.eq_form == ENTERP_EQ_NORMALIZED) {
+      step = R(1) / len1;
+      offset = R(0);
+    } else if (d.eq_form == ENTERP_EQ_DISTANCE) {
+      step = (R)d.eq_b;
+      offset = (R)d.eq_a;
+    } else {
+      const R start = (R)d.eq_a, end = (R)d.eq_b;
+      step = (end - start) / len1;
+      offset = start;
+    }
+    for (uint64_t i = 0; i < s.inner_len; ++i) {
+      const R prod = step * (R)i;
+      inner[i] = prod + offset;
+    }
+    r.eq_step = step;
+    r.eq_offset = offset;
+  }
+  // knot store + offsets (see resolve.hpp)
+  std::vector<R> store;
+  if (s.adaptor == AD_BORDER_BUFFER) {
+    // BorderBuffer::eval (src/bspline/adaptors.rs:47-50)
+    store.resize(s.virt_len);
+    for (uint64_t i = 0; i < s.virt_len; ++i) {
+      uint64_t c = i < s.border_n ? s.border_n : i;
+      if (c > s.inner_len + s.border_n - 1) c = s.inner_len + s.border_n - 1;
+      store[i] = inner[c - s.border_n];
+    }
+    r.vk_off = 0;
+    r.ik_off = (uint32_t)s.border_n;
+  } else if (s.adaptor == AD_BORDER_DELETION) {
+    store = inner;  // BorderDeletion::eval(i) = inner[i + 1] (adaptors.rs:116-118)
+    r.vk_off = 1;
+    r.ik_off = 0;
+  } else {
+    store = inner;
+    r.vk_off = r.ik_off = 0;
+  }
+  r.n_store = store.size();
+  r.store.resize(store.size() * sizeof(R));
+  std::memcpy(r.store.data(), store.data(), r.store.size());
+  const R* vk = store.data() + r.vk_off;
+
+  // search bounds on the inner chain + map back (adaptors.rs:21-39, 66-77, 137-145)
+  if (d.kind == ENTERP_BSPLINE) {
+    const uint64_t lo = s.degree, hi = s.virt_len - s.degree;  // src/bspline/mod.rs:148-149
+    if (s.adaptor == AD_BORDER_BUFFER) {
+      auto map_into = [&](uint64_t i) -> uint64_t {
+        if (i < s.border_n) return 0;
+        if (i - s.border_n >= s.inner_len) return s.inner_len;
+        return i - s.border_n;
+      };
+      r.imin = map_into(lo);
+      r.imax = map_into(hi);
+      r.map_add = (int64_t)s.border_n;
+      r.map0 = 0;
+      r.mapL = s.virt_len;
+    } else if (s.adaptor == AD_BORDER_DELETION) {
+      r.imin = lo + 1;
+      r.imax = hi + 1;
+      r.map_add = -1;
+      r.map0 = 0;  // unreachable: imin >= 1
+      r.mapL = s.inner_len - 1;
+    } else {
+      r.imin = lo;
+      r.imax = hi;
+      r.map_add = 0;
+      r.map0 = 0;
+      r.mapL = s.inner_len;
+    }
+    r.domain[0] = vk[s.degree - 1];           // src/bspline/mod.rs:180-185
+    r.domain[1] = vk[s.virt_len - s.degree];
+  } else {
+    r.imin = 0;
+    r.imax = s.inner_len;  // strict_upper_bound over the whole chain (list.rs:104-109)
+    r.map_add = 0;
+    r.map0 = 0;
+    r.mapL = s.inner_len;
+    r.domain[0] = vk[0];                      // src/linear/mod.rs:139-141
+    r.domain[1] = vk[s.virt_len - 1];
+  }
+  if (d.knot_base == ENTERP_KNOTS_EQUIDISTANT) r.eq_first = inner[r.imin < s.inner_len ? r.imin : s.inner_len - 1];
+
+  // 32-ary pivot pyramid for the sorted search
+  if (d.knot_base == ENTERP_KNOTS_SORTED) {
+    const uint64_t W = r.imax - r.imin;
+    std::vector<std::vector<R>> lv;
+    std::vector<R> cur((W + 31) / 32 * 32, nan);
+    if (cur.empty()) cur.assign(32, nan);
+    for (uint64_t i = 0; i < W; ++i) cur[i] = inner[r.imin + i];
+    lv.push_back(cur);
+    while (lv.back().size() > 32) {
+      const std::vector<R>& below = lv.back();
+      const uint64_t blocks = below.size() / 32;
+      std::vector<R> up((blocks + 31) / 32 * 32, nan);
+      for (uint64_t b = 0; b < blocks; ++b) up[b] = below[32 * b + 31];  // NaN if the block is partial
+      lv.push_back(up);
+    }
+    for (size_t i = lv.size(); i-- > 0;) {
+      std::vector<unsigned char> raw(lv[i].size() * sizeof(R));
+      std::memcpy(raw.data(), lv[i].data(), raw.size());
+      r.levels.level.push_back(std::move(raw));
+    }
+  }
+
+  // de Boor denominators all powers of two? (x / 2^k == x * 2^-k bit for bit)
+  r.pow2_denominators = 0;
+  if (d.kind == ENTERP_BSPLINE && s.degree <= 7 && s.virt_len <= (1u << 22)) {
+    const uint64_t p = s.degree, lo = s.degree, hi = s.virt_len - s.degree;
+    bool all = true;
+    for (uint64_t idx = lo; idx <= hi && all; ++idx) {
+      const bool reachable = idx == lo || idx == hi || vk[idx - 1] < vk[idx];
+      if (!reachable) continue;
+      const R* kn = vk + (idx - p);
+      for (uint64_t rr = 1; rr <= p && all; ++rr)
+        for (uint64_t j = 0; j + rr <= p; ++j) {
+          const R den = kn[p + j] - kn[j + rr - 1];
+          // keep the reciprocal a normal number so that the multiply cannot under/overflow differently
+          if (!is_pow2(den) || den < R(1e-30) || den > R(1e30)) {
+            all = false;
+            break;
+          }
+        }
+    }
+    r.pow2_denominators = all ? 1 : 0;
+  }
+}
+
+}  // namespace
+
+enterp_status validate(const enterp_curve_desc& d, int stage, enterp_error_info* err) {
+  Shape s;
+  Fail f = run_stages(d, stage, s);
+  report(f, err);
+  return f.status;
+}
+
+enterp_status resolve(const enterp_curve_desc& d, Resolved& out, enterp_error_info* err) {
+  Shape s;
+  Fail f = run_stages(d, STAGE_SPACE, s);
+  report(f, err);
+  if (f.status) return f.status;
+  out = Resolved{};
+  out.kind = d.kind;
+  out.scalar = d.scalar;
+  out.dim = d.dim;
+  out.weighted = d.weighted ? 1 : 0;
+  out.dh = d.dim + out.weighted;
+  out.knot_base = d.kind == ENTERP_BEZIER ? -1 : d.knot_base;
+  out.adaptor = s.adaptor;
+  out.n_elem = d.n_elements;
+  out.border_n = s.border_n;
+  out.inner_len = s.inner_len;
+  out.virt_len = s.virt_len;
+  out.degree = s.degree;
+  out.space_len = s.space_len;
+  if (d.scalar == ENTERP_F32)
+    build_tables<float>(d, s, out);
+  else
+    build_tables<double>(d, s, out);
+  return ENTERP_OK;
+}
+
+}  // namespace enterp

@@ -1,0 +1,63 @@
+// Host-side "builder" of the engine: validates an enterp_curve_desc with the reference's builder
+// rules and materialises the tables the kernels read. Product code (no oracle involvement).
+//
+// Unlike the reference, which keeps knot chains lazy (Equidistant recomputes step*i+offset at every
+// access, BorderBuffer/BorderDeletion remap indices at every access), the engine TABULATES the
+// virtual knot vector once at build time. Each table entry is produced by the very same IEEE
+// operations the reference would execute per access (this file is compiled with
+// -ffp-contract=off), so the tabulated values are bit-identical to the recomputed ones.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/enterp.h"
+
+namespace enterp {
+
+enum Adaptor : int32_t { AD_NONE = 0, AD_BORDER_BUFFER = 1, AD_BORDER_DELETION = 2 };
+enum Stage : int32_t { STAGE_ELEMENTS = 0, STAGE_KNOTS = 1, STAGE_SPACE = 2 };
+
+struct SearchLevels {
+  // 32-ary pivot pyramid over the searched inner knot range, top level first; every level is
+  // padded to a multiple of 32 entries with NaN (NaN <= x is false, so padding never counts).
+  std::vector<std::vector<unsigned char>> level;  // raw R values
+};
+
+struct Resolved {
+  int32_t kind = 0, scalar = 0, dim = 0, weighted = 0;
+  int32_t dh = 0;          // components carried through the recursion: dim + weighted
+  int32_t knot_base = -1;  // ENTERP_KNOTS_SORTED | ENTERP_KNOTS_EQUIDISTANT | -1 (Bezier)
+  int32_t adaptor = AD_NONE;
+  uint64_t n_elem = 0;
+  uint64_t border_n = 0;
+  uint64_t inner_len = 0;  // innermost knot chain length
+  uint64_t virt_len = 0;   // K::len()
+  uint64_t degree = 0;
+  uint64_t space_len = 0;
+  // knot store: SORTED+none/EQUI+none: virtual == inner == store; BorderBuffer: store = virtual
+  // (inner j at store[j + border_n]); BorderDeletion: store = inner (virtual i at store[i + 1]).
+  std::vector<unsigned char> store;  // raw R
+  uint64_t n_store = 0;
+  uint32_t vk_off = 0, ik_off = 0;
+  // span search bounds on the inner chain and the map back to virtual indices
+  uint64_t imin = 0, imax = 0;
+  int64_t map_add = 0;
+  uint64_t map0 = 0, mapL = 0;
+  double eq_step = 0, eq_offset = 0, eq_first = 0;  // exact R values widened to double
+  // elements, lifted to homogeneous form when weighted: [n_elem][dh]
+  std::vector<unsigned char> elems;
+  SearchLevels levels;
+  double domain[2] = {0, 0};
+  // Bezier TransformInput (base/adaptors.rs:137-139)
+  int32_t has_transform = 0;
+  double in_add = 0, in_mul = 1;
+  // every de Boor denominator reachable from [lo, hi] is a non-zero power of two
+  int32_t pow2_denominators = 0;
+};
+
+// Validates up to and including `stage`; fills `err` like the reference's error structs.
+enterp_status validate(const enterp_curve_desc& d, int stage, enterp_error_info* err);
+// Full validation + table construction.
+enterp_status resolve(const enterp_curve_desc& d, Resolved& out, enterp_error_info* err);
+
+}  // namespace enterp

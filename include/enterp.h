@@ -1,0 +1,211 @@
+/*
+ * enterp.h — C ABI of the B200-native batched curve-evaluation engine for enterpolation 0.3.0.
+ *
+ * The reference (/root/reference, 100 % Rust) has no FFI of its own; its "operator API" for the hot
+ * path is the trait surface
+ *     Signal<R>::eval / extract / sample   src/base/signal.rs:15-19, 48-58, 166-173
+ *     Curve<R>::domain / take              src/base/signal.rs:194, 221-228
+ * reached through the typestate builders
+ *     Linear::builder()                    src/linear/mod.rs:105      (src/linear/builder.rs)
+ *     Bezier::builder()                    src/bezier/mod.rs:207      (src/bezier/builder.rs)
+ *     BSpline::builder()                   src/bspline/mod.rs:115     (src/bspline/builder.rs)
+ *     Weighted<..> (NURBS)                 src/weights/weighted.rs:28-37
+ * Every entry point below states which of those it stands in for. A Rust `-sys` crate would bind
+ * exactly these symbols; in this repo the callers are the C++ fluent mirror
+ * (include/enterpolation.hpp) and the Python ctypes mirror (enterpolation_b200/).
+ *
+ * Conventions
+ *  - plain C, no torch / CUDA types in signatures: device pointers are `void*`, streams are
+ *    `void*` (a cudaStream_t, NULL = legacy default stream);
+ *  - the caller owns every host array (copied during create: "upload once") and every device
+ *    buffer; the library owns only the opaque handle;
+ *  - a handle is immutable after create; concurrent calls from several host threads are allowed
+ *    (mirrors `eval(&self)` re-entrancy, src/base/space.rs:63-66);
+ *  - outputs are dense AoS `[n][dim]` of the curve scalar (weighted curves emit the `dim`
+ *    projected components, src/weights/homogeneous.rs:134-136);
+ *  - where the reference would panic (NaN/inf/negative into `to_usize().unwrap()`,
+ *    src/base/list.rs:456,486,539-540) the device writes NaN into every component of that sample
+ *    and bumps a per-curve counter readable with enterp_invalid_count();
+ *  - no CPU fallback exists: every eval entry point returns ENTERP_NO_DEVICE / ENTERP_CUDA_ERROR
+ *    when no B200 is usable.
+ */
+#ifndef ENTERP_H_
+#define ENTERP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define ENTERP_API
+#else
+#define ENTERP_API __attribute__((visibility("default")))
+#endif
+
+typedef struct enterp_curve enterp_curve; /* opaque; immutable after create; owns device replicas */
+
+/* Error taxonomy = union of LinearError (src/linear/error.rs:13-20), BezierError
+ * (src/bezier/error.rs:12-17) and BSplineError (src/bspline/error.rs:16-31), plus ABI-level codes. */
+typedef enum enterp_status {
+  ENTERP_OK = 0,
+  ENTERP_TOO_FEW_ELEMENTS = 1,            /* builder.rs:107  */
+  ENTERP_TOO_FEW_KNOTS = 2,               /* builder.rs:135  */
+  ENTERP_KNOT_ELEMENT_INEQUALITY = 3,     /* linear/error.rs:56 */
+  ENTERP_NOT_SORTED = 4,                  /* base/list.rs:325 */
+  ENTERP_INCONGRUOUS_ELEMENTS_KNOTS = 5,  /* bspline/error.rs:132 */
+  ENTERP_INCONGRUOUS_ELEMENTS_DEGREE = 6, /* bspline/error.rs:202 */
+  ENTERP_INVALID_DEGREE = 7,              /* bspline/error.rs:95 */
+  ENTERP_TOO_SMALL_WORKSPACE = 8,         /* builder.rs:163 */
+  ENTERP_EMPTY = 9,                       /* builder.rs:85 */
+  ENTERP_INVALID_ARGUMENT = 10,           /* malformed descriptor / NULL pointer / bad enum */
+  ENTERP_UNSUPPORTED = 11,                /* combination the reference has no impl block for */
+  ENTERP_NO_DEVICE = 12,                  /* no CUDA device / device index out of range */
+  ENTERP_CUDA_ERROR = 13                  /* a CUDA runtime call failed; see enterp_last_cuda_error */
+} enterp_status;
+
+enum { ENTERP_LINEAR = 0, ENTERP_BEZIER = 1, ENTERP_BSPLINE = 2 };           /* desc.kind      */
+enum { ENTERP_F32 = 0, ENTERP_F64 = 1 };                                       /* desc.scalar    */
+enum { ENTERP_OPEN = 0, ENTERP_CLAMPED = 1, ENTERP_LEGACY = 2 };               /* desc.mode      */
+enum { ENTERP_KNOTS_SORTED = 0, ENTERP_KNOTS_EQUIDISTANT = 1 };                /* desc.knot_base */
+enum { ENTERP_EQ_BY_DEGREE = 0, ENTERP_EQ_BY_QUANTITY = 1 };                   /* desc.eq_by     */
+enum { ENTERP_EQ_DOMAIN = 0, ENTERP_EQ_NORMALIZED = 1, ENTERP_EQ_DISTANCE = 2 }; /* desc.eq_form */
+enum { ENTERP_SPACE_CONSTANT = 0, ENTERP_SPACE_DYNAMIC = 1, ENTERP_SPACE_WORKSPACE = 2 }; /* desc.space */
+enum { ENTERP_INPUT_NORMALIZED = 0, ENTERP_INPUT_DOMAIN = 1 };                 /* desc.input_form (Bezier) */
+
+/* One descriptor == one finished builder chain. The fields mirror the typestate the reference's
+ * builders resolve to; validation happens in the order the builder methods are called in
+ * (elements -> knots|equidistant.degree|quantity -> domain|normalized|distance -> space). */
+typedef struct enterp_curve_desc {
+  int32_t kind;      /* ENTERP_LINEAR | ENTERP_BEZIER | ENTERP_BSPLINE */
+  int32_t scalar;    /* ENTERP_F32 | ENTERP_F64: type R of knots, parameters and element components */
+  int32_t dim;       /* 1..4 components per element (f32/f64 scalar or [R;2..4]) */
+  int32_t weighted;  /* 0: .elements(E); 1: .elements_with_weights(G) -> Weighted<..> output is projected */
+  uint64_t n_elements;
+  const void* elements; /* host AoS [n_elements][dim] of R */
+  const void* weights;  /* host [n_elements] of R, or NULL when !weighted */
+
+  int32_t mode;      /* BSpline: ENTERP_OPEN (default) | ENTERP_CLAMPED | ENTERP_LEGACY */
+  int32_t knot_base; /* ENTERP_KNOTS_SORTED: .knots(K); ENTERP_KNOTS_EQUIDISTANT: .equidistant::<R>() */
+  uint64_t n_knots;  /* SORTED only */
+  const void* knots; /* SORTED only: host [n_knots] of R exactly as the user gave them */
+
+  int32_t eq_by;     /* BSpline+EQUIDISTANT: .degree(eq_count) or .quantity(eq_count) */
+  int32_t eq_form;   /* .domain(eq_a, eq_b) | .normalized() | .distance(start = eq_a, step = eq_b) */
+  uint64_t eq_count;
+  double eq_a, eq_b; /* carried as f64; converted to R exactly when R = f32 values were given */
+
+  int32_t space;        /* .constant::<N>() | .dynamic() | .workspace(S): BSpline and Bezier */
+  int32_t input_form;   /* Bezier: .normalized::<R>() | .domain(in_a, in_b) (TransformInput) */
+  uint64_t workspace_n; /* N of constant::<N>() / S.len() of workspace(S); ignored for dynamic */
+  double in_a, in_b;
+} enterp_curve_desc;
+
+/* Payload of the reference's error structs (found/necessary, elements/knots, index, degree). */
+typedef struct enterp_error_info {
+  int32_t status;
+  int32_t mode;        /* build mode reported by IncongruousElements* (bspline/error.rs:124-130) */
+  uint64_t found;      /* TooFew*: found; TooSmallWorkspace: found; InvalidDegree: degree;
+                          KnotElementInequality/Incongruous*: number of elements */
+  uint64_t necessary;  /* TooSmallWorkspace: necessary; KnotElementInequality/IncongruousElementsKnots:
+                          number of knots; IncongruousElementsDegree: degree */
+  uint64_t index;      /* NotSorted: index (list.rs:327) */
+} enterp_error_info;
+
+/* Resolved shape of a built curve (what the Rust type would carry). */
+typedef struct enterp_curve_info {
+  int32_t kind, scalar, dim, weighted;
+  int32_t knot_base;     /* SORTED | EQUIDISTANT | -1 (Bezier) */
+  int32_t adaptor;       /* 0 none, 1 BorderBuffer, 2 BorderDeletion (bspline/adaptors.rs) */
+  uint64_t n_elements;
+  uint64_t n_knots;      /* virtual knot count = K::len() of the built curve */
+  uint64_t degree;       /* BSpline: n_knots - n_elements + 1 (bspline/mod.rs:254); Bezier: n-1; Linear: 1 */
+  uint64_t border;       /* BorderBuffer n */
+  double domain[2];      /* Curve::domain() */
+} enterp_curve_info;
+
+/* ---- construction: *::builder()...build() ------------------------------------------------- */
+
+/* Validates the descriptor with the reference's builder rules and resolves it on the host (no CUDA
+ * call). On error *out is NULL, the first failing builder step is reported like the Director
+ * variants do (src/bspline/builder.rs:225-241, 377-401, 447-466, 512-534, 633-692, 780-836,
+ * 1087-1130; src/linear/builder.rs:165-181, 325-340; src/bezier/builder.rs:134-150, 354-367). */
+/* Director semantics: validate only the builder steps up to `stage` (0 = elements, 1 = knots,
+ * 2 = workspace/everything) so that a host wrapper can fail AT the offending call like the
+ * reference's `*Director` types do (e.g. src/bspline/builder.rs:225-241). */
+ENTERP_API enterp_status enterp_curve_validate(const enterp_curve_desc* desc, int stage,
+                                               enterp_error_info* err /* may be NULL */);
+ENTERP_API enterp_status enterp_curve_create(const enterp_curve_desc* desc, enterp_curve** out,
+                                             enterp_error_info* err /* may be NULL */);
+ENTERP_API void enterp_curve_destroy(enterp_curve* curve);
+ENTERP_API enterp_status enterp_curve_get_info(const enterp_curve* curve, enterp_curve_info* info);
+/* Curve::domain(): linear/mod.rs:139-141, bspline/mod.rs:180-185, bezier/mod.rs:257-259,
+ * base/adaptors.rs:161-166 (TransformInput). */
+ENTERP_API enterp_status enterp_curve_domain(const enterp_curve* curve, double out[2]);
+/* Replicates the resolved tables onto `device` ("uploaded once"). Implicit on first eval. */
+ENTERP_API enterp_status enterp_curve_upload(enterp_curve* curve, int device);
+
+/* ---- evaluation over device-resident buffers ---------------------------------------------- */
+
+/* Signal::sample(iter): out[i] = curve.eval(t[i]); t_dev [n] of R, out_dev [n][dim] of R. */
+ENTERP_API enterp_status enterp_eval_batch(enterp_curve* curve, int device, const void* t_dev,
+                                           uint64_t n, void* out_dev, void* stream);
+/* Curve::take(n_total) restricted to global sample indices [first, first+count): the stepper
+ * t_i = step*fl(i)+start with step=(end-start)/fl(n_total-1) (list.rs:393-399, 416-418) is
+ * generated on the device from the GLOBAL index, so shards of one take() agree bit for bit. */
+ENTERP_API enterp_status enterp_eval_take(enterp_curve* curve, int device, uint64_t n_total,
+                                          uint64_t first, uint64_t count, void* out_dev,
+                                          void* stream);
+/* Parity/debug: the knot-span decision only. BSpline: idx[i] = strict_upper_bound_clamped(t,
+ * degree, len-degree) (bspline/mod.rs:148-154); Linear: idx[i] = max_index of upper_border
+ * (list.rs:169-203, 532-551); Bezier: 0. factor_dev (may be NULL) receives Linear's factor. */
+ENTERP_API enterp_status enterp_span_batch(enterp_curve* curve, int device, const void* t_dev,
+                                           uint64_t n, uint32_t* idx_dev, void* factor_dev,
+                                           void* stream);
+ENTERP_API enterp_status enterp_span_take(enterp_curve* curve, int device, uint64_t n_total,
+                                          uint64_t first, uint64_t count, uint32_t* idx_dev,
+                                          void* factor_dev, void* stream);
+/* The take() parameter values themselves (Stepper, signal.rs:607-609). */
+ENTERP_API enterp_status enterp_stepper(int scalar, int device, double start, double end,
+                                        uint64_t n_total, uint64_t first, uint64_t count,
+                                        void* t_out_dev, void* stream);
+/* Many independent Bezier curves sharing one take(samples_per_curve) table on [0,1]:
+ * ctrl_dev [n_curves][n_ctrl][dim] of R -> out_dev [n_curves][samples_per_curve][dim].
+ * Equivalent to building n_curves `Bezier::builder().elements(ctrl[c]).normalized().constant()`
+ * curves and collecting `.take(samples_per_curve)` of each (bezier/mod.rs:240-246). */
+ENTERP_API enterp_status enterp_bezier_many_take(int scalar, int dim, uint64_t n_curves,
+                                                 uint32_t n_ctrl, const void* ctrl_dev,
+                                                 uint32_t samples_per_curve, int device,
+                                                 void* out_dev, void* stream);
+
+/* ---- evaluation with HOST buffers (the call a user of the reference makes) ----------------- */
+
+/* `curve.sample(t).collect::<Vec<_>>()`: pageable or pinned host in/out, chunked and pipelined
+ * H2D -> kernel -> D2H on two streams; blocks until out_host is complete. */
+ENTERP_API enterp_status enterp_sample_host(enterp_curve* curve, int device, const void* t_host,
+                                            uint64_t n, void* out_host);
+/* `curve.take(n_total).skip(first).take(count).collect()`. */
+ENTERP_API enterp_status enterp_take_host(enterp_curve* curve, int device, uint64_t n_total,
+                                          uint64_t first, uint64_t count, void* out_host);
+/* Pinned host memory for zero-staging transfers of the two calls above. */
+ENTERP_API enterp_status enterp_host_alloc(void** ptr, uint64_t bytes);
+ENTERP_API void enterp_host_free(void* ptr);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+
+/* Number of samples so far (on `device`) for which the reference would have panicked. */
+ENTERP_API enterp_status enterp_invalid_count(enterp_curve* curve, int device,
+                                              unsigned long long* n);
+ENTERP_API const char* enterp_status_str(enterp_status status);
+ENTERP_API const char* enterp_last_cuda_error(void);
+ENTERP_API int enterp_device_count(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+ENTERP_API unsigned long long enterp_launch_count(void);
+ENTERP_API const char* enterp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENTERP_H_ */
