@@ -1,0 +1,240 @@
+"""Differential parity: CUDA path (through the C ABI) vs the CPU oracle on seeded random and
+adversarial inputs. Bar (BASELINE.json north_star): span indices bit-exact, f64 within 4 ulp, f32
+within 1e-6 relative. The kernels are built from unfused IEEE operations in the reference's order,
+so the tests demand the stronger property: bit-for-bit equality (any NaN == any NaN)."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from enterpolation_b200 import Bezier, BSpline, Linear, _abi, bezier_many_take, stepper_device
+from oracle import oracle
+
+from util import assert_bits_equal, u01
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f32": np.float32, "f64": np.float64}
+
+
+def adversarial(knots, dtype, rng, n_random=3000):
+    """Exact knots, their nextafter neighbours, out-of-domain values, +-0, denormals, huge values."""
+    k = np.unique(np.asarray(knots, dtype=dtype))
+    lo, hi = k[0], k[-1]
+    span = max(float(hi - lo), 1.0)
+    parts = [k, np.nextafter(k, dtype(np.inf)), np.nextafter(k, dtype(-np.inf)),
+             np.array([0.0, -0.0, np.finfo(dtype).tiny, -np.finfo(dtype).tiny, np.finfo(dtype).tiny / 4,
+                       lo - span, hi + span, lo - 1e6, hi + 1e6, np.finfo(dtype).max / 8, -np.finfo(dtype).max / 8],
+                      dtype=dtype),
+             rng.uniform(float(lo) - 0.25 * span, float(hi) + 0.25 * span, n_random).astype(dtype)]
+    return np.concatenate(parts).astype(dtype)
+
+
+def check_curve(builder, t, take_n=777, what=""):
+    curve = builder.build()
+    ref = oracle.OracleCurve(builder.to_desc())
+    tt = torch.from_numpy(np.ascontiguousarray(t)).cuda()
+    before = curve.invalid_count()
+    got = curve.sample_device(tt).cpu().numpy()
+    want, inv = ref.eval(t, return_invalid=True)
+    assert_bits_equal(got, want, what + " batch")
+    assert curve.invalid_count() - before == inv, what + " invalid counter"
+    idx, fac = curve.span_device(tt)
+    widx, wfac = ref.span(t)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32), widx), what + " span indices"
+    assert_bits_equal(fac.cpu().numpy(), wfac, what + " span factor")
+    # take(): whole, and a shard with a non-zero global offset
+    got = curve.take_device(take_n).cpu().numpy()
+    assert_bits_equal(got, ref.take(take_n), what + " take")
+    lo, cnt = take_n // 3, take_n // 2
+    assert_bits_equal(curve.take_device(take_n, lo, cnt).cpu().numpy(), ref.take(take_n, lo, cnt), what + " take shard")
+    # host-buffer entry points (the call a user of the reference makes)
+    assert_bits_equal(np.asarray(curve.sample(t)), want, what + " sample_host")
+    assert_bits_equal(np.asarray(curve.take(take_n).collect()), ref.take(take_n), what + " take_host")
+    return curve, ref
+
+
+def rand_elements(n, dim, dtype, seed):
+    e = (u01(n * dim, seed, dtype) * dtype(2) - dtype(1)).astype(dtype)
+    return e.reshape(n, dim) if dim > 1 else e
+
+
+def sorted_knots(n, dtype, seed, repeat_every=0):
+    k = np.cumsum(0.5 + u01(n, seed, np.float64)).astype(dtype)
+    if repeat_every:
+        for i in range(repeat_every, n, repeat_every):
+            k[i] = k[i - 1]
+    return k
+
+
+@pytest.mark.parametrize("scalar,dim,weighted", [(s, d, w) for s in ("f32", "f64") for d in (1, 2, 3, 4) for w in (0, 1)])
+@pytest.mark.parametrize("degree", [1, 2, 3, 5, 7, 9])
+def test_bspline_sorted_open(scalar, dim, weighted, degree):
+    dtype = DT[scalar]
+    rng = np.random.default_rng(degree * 100 + dim * 10 + weighted)
+    e = degree + 12
+    k = e + degree - 1
+    knots = sorted_knots(k, dtype, 0xE2 + degree, repeat_every=5)
+    el = rand_elements(e, dim, dtype, 0xE1 + dim)
+    b = BSpline.builder()
+    b = b.elements_with_weights(el, (0.5 + u01(e, 0xE3, dtype)).astype(dtype)) if weighted else b.elements(el)
+    b = b.knots(knots)
+    b = b.constant(degree + 1) if degree % 2 else b.dynamic()
+    check_curve(b, adversarial(knots, dtype, rng), what=f"bspline sorted {scalar} d{dim} w{weighted} p{degree}")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("mode", ["clamped", "legacy"])
+@pytest.mark.parametrize("degree", [1, 2, 3, 4])
+def test_bspline_sorted_modes(scalar, mode, degree):
+    dtype = DT[scalar]
+    rng = np.random.default_rng(degree)
+    e = degree + 9
+    if mode == "clamped":
+        k = e - degree + 1  # BorderBuffer n = e - k = degree - 1
+        b = BSpline.builder().clamped()
+    else:
+        k = e + degree + 1  # legacy: textbook knot vector
+        b = BSpline.builder().legacy()
+    knots = sorted_knots(k, dtype, 0xA0 + degree)
+    b = b.elements(rand_elements(e, 3, dtype, 0xA1)).knots(knots).constant(degree + 1)
+    curve, _ = check_curve(b, adversarial(knots, dtype, rng), what=f"bspline {mode} {scalar} p{degree}")
+    assert curve.degree == degree
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("mode", ["open", "clamped"])
+@pytest.mark.parametrize("form", ["domain", "normalized", "distance"])
+@pytest.mark.parametrize("degree,dim,weighted", [(1, 1, 0), (2, 2, 1), (3, 4, 0), (3, 3, 1), (4, 1, 1), (6, 2, 0)])
+def test_bspline_equidistant(scalar, mode, form, degree, dim, weighted):
+    dtype = DT[scalar]
+    rng = np.random.default_rng(degree * 7 + dim)
+    e = degree + 8
+    el = rand_elements(e, dim, dtype, 0xB1 + degree)
+    b = BSpline.builder()
+    b = b.clamped() if mode == "clamped" else b.open()
+    b = b.elements_with_weights(el, (0.5 + u01(e, 0xB3, dtype)).astype(dtype)) if weighted else b.elements(el)
+    b = b.equidistant(scalar).degree(degree)
+    if form == "domain":
+        b = b.domain(-2.0, 3.0)
+    elif form == "normalized":
+        b = b.normalized()
+    else:
+        b = b.distance(0.25, 0.3)
+    b = b.constant(degree + 1) if degree != 2 else b.dynamic()
+    ref = oracle.OracleCurve(b.to_desc())
+    d = ref.domain()
+    n_inner = e - 1 + degree if mode == "open" else e - degree + 1
+    approx_knots = np.linspace(float(d[0]), float(d[1]), 4 * n_inner + 1)
+    t = adversarial(approx_knots, dtype, rng)
+    t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf], dtype=dtype)])  # reference panics on NaN/+inf
+    check_curve(b, t, what=f"bspline equi {scalar} {mode} {form} p{degree} d{dim} w{weighted}")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("dim,weighted", [(1, 0), (3, 0), (2, 1), (4, 1)])
+@pytest.mark.parametrize("knots_kind", ["sorted", "sorted_repeats", "domain", "normalized", "distance"])
+def test_linear(scalar, dim, weighted, knots_kind):
+    dtype = DT[scalar]
+    rng = np.random.default_rng(dim)
+    e = 37
+    el = rand_elements(e, dim, dtype, 0xC1)
+    b = Linear.builder()
+    b = b.elements_with_weights(el, (0.5 + u01(e, 0xC3, dtype)).astype(dtype)) if weighted else b.elements(el)
+    if knots_kind.startswith("sorted"):
+        knots = sorted_knots(e, dtype, 0xC2, repeat_every=4 if knots_kind == "sorted_repeats" else 0)
+        if knots_kind == "sorted_repeats":
+            knots[1] = knots[0]
+            knots[-2] = knots[-1]  # coincident edge knots: linear_factor returns the zero difference
+        b = b.knots(knots)
+        t = adversarial(knots, dtype, rng)
+        t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+    else:
+        b = b.equidistant(scalar)
+        b = {"domain": lambda: b.domain(-1.0, 4.0), "normalized": lambda: b.normalized(),
+             "distance": lambda: b.distance(2.0, 0.125)}[knots_kind]()
+        d = oracle.OracleCurve(b.to_desc()).domain()
+        t = adversarial(np.linspace(float(d[0]), float(d[1]), 4 * (e - 1) + 1), dtype, rng)
+        t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+    check_curve(b, t, what=f"linear {scalar} d{dim} w{weighted} {knots_kind}")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 8, 16, 17, 40])
+@pytest.mark.parametrize("dim,weighted,domain", [(1, 0, None), (3, 0, None), (2, 1, None), (4, 1, (0.0, 2.0)), (3, 0, (1.0, 3.0))])
+def test_bezier(scalar, n, dim, weighted, domain):
+    dtype = DT[scalar]
+    rng = np.random.default_rng(n)
+    el = rand_elements(n, dim, dtype, 0xD1 + n)
+    b = Bezier.builder()
+    b = b.elements_with_weights(el, (0.5 + u01(n, 0xD3, dtype)).astype(dtype)) if weighted else b.elements(el)
+    b = b.domain(domain[0], domain[1], scalar) if domain else b.normalized(scalar)
+    b = b.constant() if n % 2 else b.dynamic()
+    t = adversarial([0.0, 0.5, 1.0, 2.0, 3.0], dtype, rng, n_random=1500)
+    check_curve(b, t, what=f"bezier {scalar} n{n} d{dim} w{weighted} dom{domain}")
+
+
+def test_weight_zero_is_a_direction():  # homogeneous.rs:83-88; bezier/builder.rs:237-245 ends in inf
+    b = Bezier.builder().elements_with_weights([(1.0, 1.0), (2.0, 4.0), (3.0, 0.0)]).normalized("f64").constant()
+    check_curve(b, np.linspace(-0.5, 1.5, 201), what="weight zero")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+def test_stepper_matches_oracle(scalar):
+    sc = _abi.F32 if scalar == "f32" else _abi.F64
+    for (a, b, n, first, count) in [(0.0, 1.0, 11, 0, 11), (3.0, 5.0, 5, 0, 5), (-2.0, 2.0, 1 << 24, (1 << 24) - 5000, 5000),
+                                    (0.0, 1.0, 1 << 32, (1 << 32) - 4096, 4096), (0.0, 1.0, 1 << 32, (1 << 31) + 12345, 4096),
+                                    (0.0, 1.0, 1, 0, 1)]:
+        got = stepper_device(sc, a, b, n, first, count).cpu().numpy()
+        assert_bits_equal(got, oracle.stepper(sc, a, b, n, first, count), f"stepper {scalar} n={n}")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("n_ctrl,dim", [(16, 3), (4, 2), (2, 1), (1, 4), (20, 3)])
+def test_bezier_many(scalar, n_ctrl, dim):
+    dtype = DT[scalar]
+    n_curves, samples = 257, 100
+    ctrl = rand_elements(n_curves * n_ctrl, dim, dtype, 0xF1).reshape(n_curves, n_ctrl, dim)
+    got = bezier_many_take(torch.from_numpy(ctrl).cuda(), samples).cpu().numpy()
+    assert_bits_equal(got, oracle.bezier_many_take(ctrl, samples), f"bezier_many {scalar} n{n_ctrl} d{dim}")
+    # each curve equals the single-curve builder path
+    c0 = Bezier.builder().elements(ctrl[5] if dim > 1 else ctrl[5, :, 0]).normalized(scalar).constant().build()
+    assert_bits_equal(np.asarray(c0.take(samples).collect()).reshape(samples, dim), got[5], "many == single")
+
+
+def test_large_sorted_search_levels():
+    """4-level pivot pyramid (70 000 knots): exact knots + neighbours + random, f32 Linear [f32;3]."""
+    dtype = np.float32
+    n = 70_000
+    knots = sorted_knots(n, dtype, 0xE2)
+    el = rand_elements(n, 3, dtype, 0xE1)
+    b = Linear.builder().elements(el).knots(knots)
+    rng = np.random.default_rng(0)
+    pick = rng.integers(0, n, 4000)
+    t = np.concatenate([knots[pick], np.nextafter(knots[pick], dtype(np.inf)), np.nextafter(knots[pick], dtype(-np.inf)),
+                        rng.uniform(knots[0] - 10, knots[-1] + 10, 50_000).astype(dtype),
+                        knots[:40], knots[-40:], np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+    check_curve(b, t.astype(dtype), take_n=5000, what="large sorted linear")
+
+
+def test_config_shapes_small():
+    """BASELINE.json configs at sizes the oracle finishes in seconds."""
+    # C1: README cardinal cubic, f64, take
+    b = BSpline.builder().clamped().elements([0.0, 0.0, 0.0, 6.0, 0.0, 0.0, 0.0]).equidistant("f64").degree(3) \
+        .domain(-2.0, 2.0).constant(4)
+    c = b.build()
+    ref = oracle.OracleCurve(b.to_desc())
+    n = 1 << 18
+    assert_bits_equal(c.take_device(n).cpu().numpy(), ref.take(n, threads=8), "C1")
+    idx, _ = c.span_take_device(n)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32), ref.span_take(n)[0])
+    # C5: dynamic clamped equidistant cubic [f32;4], global n = 2^32, windows at both ends and the middle
+    for stops in (5, 256):
+        el = u01(stops * 4, 0xE1, np.float32).reshape(stops, 4)
+        b = BSpline.builder().clamped().elements(el).equidistant("f32").degree(3).normalized().dynamic()
+        c = b.build()
+        ref = oracle.OracleCurve(b.to_desc())
+        for first in (0, (1 << 31) - 50_000, (1 << 32) - 100_000):
+            assert_bits_equal(c.take_device(1 << 32, first, 100_000).cpu().numpy(), ref.take(1 << 32, first, 100_000, threads=8),
+                              f"C5 stops={stops} first={first}")
