@@ -3,6 +3,7 @@
 // in the library: every eval entry point ends in a kernel launch or an error status.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -31,6 +32,12 @@ int sm_count() {
   }
   return cache[dev];
 }
+
+// Debug/ablation switch (env ENTERP_DISABLE_ROWS=1): route B-splines through the generic kernel.
+static const bool g_disable_rows = [] {
+  const char* v = std::getenv("ENTERP_DISABLE_ROWS");
+  return v && v[0] == '1';
+}();
 
 static thread_local std::string t_cuda_error;
 static enterp_status cuda_fail(cudaError_t e, const char* where) {
@@ -73,6 +80,7 @@ struct Replica {
   int device = -1;
   void* store = nullptr;
   void* elems = nullptr;
+  void* rows = nullptr;
   void* lvl[MAX_LEVELS] = {};
   int n_lvl = 0;
   unsigned long long* invalid = nullptr;
@@ -116,6 +124,7 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   };
   cudaError_t e = put(c->r.store, &rp->store);
   if (e == cudaSuccess) e = put(c->r.elems, &rp->elems);
+  if (e == cudaSuccess && c->r.rows_mode) e = put(c->r.rows, &rp->rows);
   rp->n_lvl = (int)c->r.levels.level.size();
   for (int l = 0; l < rp->n_lvl && e == cudaSuccess; ++l) e = put(c->r.levels.level[l], &rp->lvl[l]);
   if (e == cudaSuccess) e = cudaMalloc((void**)&rp->invalid, sizeof(unsigned long long));
@@ -123,6 +132,7 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   if (e != cudaSuccess) {
     cudaFree(rp->store);
     cudaFree(rp->elems);
+    cudaFree(rp->rows);
     for (int l = 0; l < MAX_LEVELS; ++l) cudaFree(rp->lvl[l]);
     cudaFree(rp->invalid);
     delete rp;
@@ -203,7 +213,20 @@ enterp_status dispatch_eval(const Resolved& r, const Replica& rp, const SampleSr
     case ENTERP_BSPLINE: {
       if (r.degree > (uint64_t)MAX_DYN_DEGREE) return ENTERP_UNSUPPORTED;
       const int deg = r.degree <= 7 ? (int)r.degree : 0;
-      e = launch_bspline<R>(r.dh, proj, deg, equi, d, s, static_cast<R*>(out), vec_ok, st);
+      if (r.rows_mode && rp.rows && deg > 0 && !g_disable_rows) {
+        // fast path: per-span rows staged in shared memory by TMA (rows.cuh)
+        RowsDev<R> rw{};
+        rw.table = static_cast<const R*>(rp.rows);
+        rw.n_rows = r.rows_n;
+        rw.lo = r.rows_lo;
+        rw.bytes = (uint32_t)r.rows.size();
+        rw.one = R(1);
+        rw.eq_rstep = (R)r.eq_rstep;
+        rw.eq_mode = r.eq_mode;
+        e = launch_bspline_rows<R>(r.dh, proj, deg, equi, r.rows_mode == 1, d, s, static_cast<R*>(out), vec_ok, rw, st);
+      } else {
+        e = launch_bspline<R>(r.dh, proj, deg, equi, d, s, static_cast<R*>(out), vec_ok, st);
+      }
       break;
     }
     case ENTERP_LINEAR:
@@ -413,6 +436,7 @@ ENTERP_API void enterp_curve_destroy(enterp_curve* c) {
     DeviceGuard g(rp->device);
     cudaFree(rp->store);
     cudaFree(rp->elems);
+    cudaFree(rp->rows);
     for (int l = 0; l < MAX_LEVELS; ++l) cudaFree(rp->lvl[l]);
     cudaFree(rp->invalid);
     for (int b = 0; b < 2; ++b) {

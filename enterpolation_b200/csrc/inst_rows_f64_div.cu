@@ -1,0 +1,9 @@
+#include "inst_rows.cuh"
+namespace enterp {
+template <>
+cudaError_t launch_bspline_rows_mode<double, false>(int dh, bool proj, int deg, bool equi, const CurveDev<double>& c,
+                                               const SampleSrc<double>& s, double* out, bool vec_ok, const RowsDev<double>& rw,
+                                               cudaStream_t st) {
+  return launch_rows_impl<double, false>(dh, proj, deg, equi, c, s, out, vec_ok, rw, st);
+}
+}  // namespace enterp

@@ -40,6 +40,18 @@ struct SampleSrc {
   unsigned long long count;  // samples in this launch
 };
 
+// Span-row table of the fast B-spline kernel (rows.cuh).
+template <class R>
+struct RowsDev {
+  const R* table;     // global copy of the row table (staged into shared memory by TMA)
+  uint32_t n_rows;    // hi - lo + 1
+  uint32_t lo;        // span index of row 0
+  uint32_t bytes;     // n_rows * row_len * sizeof(R), multiple of 16
+  R one;              // 1.0, opaque to the compiler (see header comment)
+  R eq_rstep;         // RN(1 / eq_step) (exact when eq_step is a power of two)
+  int eq_mode;        // equidistant span division: 0 IEEE div, 1 exact inverse multiply, 2 Markstein
+};
+
 // ---- exact arithmetic -------------------------------------------------------------------------
 __device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }

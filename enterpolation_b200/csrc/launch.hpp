@@ -30,6 +30,17 @@ int grid_for(K kernel, unsigned long long work_items, int items_per_block) {
 template <class R>
 cudaError_t launch_bspline(int dh, bool proj, int deg, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
                            bool vec_ok, cudaStream_t st);
+// Span-row fast path (rows.cuh): deg 1..7, table <= ROWS_MAX_BYTES. POW2: exact inverse multiply.
+template <class R, bool POW2>
+cudaError_t launch_bspline_rows_mode(int dh, bool proj, int deg, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s,
+                                     R* out, bool vec_ok, const RowsDev<R>& rw, cudaStream_t st);
+template <class R>
+inline cudaError_t launch_bspline_rows(int dh, bool proj, int deg, bool equi, bool pow2, const CurveDev<R>& c,
+                                       const SampleSrc<R>& s, R* out, bool vec_ok, const RowsDev<R>& rw,
+                                       cudaStream_t st) {
+  return pow2 ? launch_bspline_rows_mode<R, true>(dh, proj, deg, equi, c, s, out, vec_ok, rw, st)
+              : launch_bspline_rows_mode<R, false>(dh, proj, deg, equi, c, s, out, vec_ok, rw, st);
+}
 template <class R>
 cudaError_t launch_linear(int dh, bool proj, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
                           cudaStream_t st);

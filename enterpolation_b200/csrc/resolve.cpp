@@ -2,6 +2,8 @@
 // reference's per-access arithmetic would produce.
 #include "resolve.hpp"
 
+#include "rows_layout.hpp"
+
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -206,6 +208,81 @@ bool is_pow2(R v) {
   return std::frexp(v, &ex) == R(0.5);
 }
 
+// Safe magnitude window of denominators for the FMA-based exact division in rows.cuh.
+template <class R>
+bool den_in_window(R v) {
+  const R lo = sizeof(R) == 4 ? R(9.5367431640625e-07) : R(6.223015277861142e-61);   // 2^-20 / 2^-200
+  const R hi = sizeof(R) == 4 ? R(1048576.0) : R(1.6069380442589903e+60);            // 2^20  / 2^200
+  return std::isfinite(v) && v >= lo && v <= hi;
+}
+
+// Span rows (see rows_layout.hpp): one row per span index in [lo, hi].
+template <class R>
+void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R* vk) {
+  r.rows_mode = 0;
+  const int p = (int)s.degree;
+  if (s.degree < 1 || s.degree > (uint64_t)ROWS_MAX_DEGREE) return;
+  const uint64_t lo = s.degree, hi = s.virt_len - s.degree;
+  const uint64_t n_rows = hi - lo + 1;
+  const int W = lanes_of<R>();
+  const int len = row_len<R>(p, r.dh);
+  if (n_rows * (uint64_t)len * sizeof(R) > ROWS_MAX_BYTES) return;
+  const bool equi = d.knot_base == ENTERP_KNOTS_EQUIDISTANT;
+  if (equi) {
+    const R step = (R)r.eq_step;
+    if (!(step > R(0)) || !std::isfinite(step)) return;  // degenerate chains keep the generic kernel
+    if (is_pow2(step) && step >= R(1e-30) && step <= R(1e30)) {
+      r.eq_mode = 1;
+      r.eq_rstep = R(1) / step;
+    } else if (den_in_window(step)) {
+      r.eq_mode = 2;
+      r.eq_rstep = R(1) / step;  // correctly rounded by the host division
+    } else {
+      r.eq_mode = 0;
+      r.eq_rstep = 0;
+    }
+  }
+  const FactorSched sch = make_sched(p, W);
+  const int nops = sch.nops;
+  const int dhp = round_up(r.dh, W);
+  const R nan = std::numeric_limits<R>::quiet_NaN();
+  std::vector<R> tab((size_t)n_rows * len, R(0));
+  const R* el = reinterpret_cast<const R*>(r.elems.data());
+  bool all_pow2 = true, all_window = true;
+  for (uint64_t idx = lo; idx <= hi; ++idx) {
+    R* row = tab.data() + (idx - lo) * len;
+    // a span strictly inside (lo, hi) is only ever selected when it has positive width
+    const bool needed = equi || idx == lo || idx == hi || vk[idx - 1] < vk[idx];
+    const R* kn = vk + (idx - p);  // kn[m] = knots[index - p + m], m = 0 .. 2p-1
+    for (int t = 0; t < nops; ++t)
+      for (int l = 0; l < W; ++l) {
+        const int rr = sch.r[t][l], j = sch.j[t][l];
+        const R left = kn[j + rr - 1];                 // knots[i - 1]
+        const R den = kn[p + j] - left;                // knots[i + p - r] - knots[i - 1]
+        if (needed) {
+          if (!(is_pow2(den) && den >= R(1e-30) && den <= R(1e30))) all_pow2 = false;
+          if (!den_in_window(den)) all_window = false;
+        }
+        row[t * W + l] = left;
+        row[nops * W + t * W + l] = needed ? R(1) / den : nan;
+        row[2 * nops * W + t * W + l] = needed ? -den : nan;
+      }
+    for (int i = 0; i <= p; ++i)
+      for (int c = 0; c < r.dh; ++c) row[3 * nops * W + i * dhp + c] = el[(idx - p + i) * r.dh + c];
+  }
+  if (all_pow2)
+    r.rows_mode = 1;
+  else if (all_window)
+    r.rows_mode = 2;
+  else
+    return;
+  r.rows_n = (uint32_t)n_rows;
+  r.rows_lo = (uint32_t)lo;
+  r.rows_len = (uint32_t)len;
+  r.rows.resize(tab.size() * sizeof(R));
+  std::memcpy(r.rows.data(), tab.data(), r.rows.size());
+}
+
 template <class R>
 void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
   const R nan = std::numeric_limits<R>::quiet_NaN();
@@ -359,27 +436,7 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
     }
   }
 
-  // de Boor denominators all powers of two? (x / 2^k == x * 2^-k bit for bit)
-  r.pow2_denominators = 0;
-  if (d.kind == ENTERP_BSPLINE && s.degree <= 7 && s.virt_len <= (1u << 22)) {
-    const uint64_t p = s.degree, lo = s.degree, hi = s.virt_len - s.degree;
-    bool all = true;
-    for (uint64_t idx = lo; idx <= hi && all; ++idx) {
-      const bool reachable = idx == lo || idx == hi || vk[idx - 1] < vk[idx];
-      if (!reachable) continue;
-      const R* kn = vk + (idx - p);
-      for (uint64_t rr = 1; rr <= p && all; ++rr)
-        for (uint64_t j = 0; j + rr <= p; ++j) {
-          const R den = kn[p + j] - kn[j + rr - 1];
-          // keep the reciprocal a normal number so that the multiply cannot under/overflow differently
-          if (!is_pow2(den) || den < R(1e-30) || den > R(1e30)) {
-            all = false;
-            break;
-          }
-        }
-    }
-    r.pow2_denominators = all ? 1 : 0;
-  }
+  if (d.kind == ENTERP_BSPLINE) build_rows<R>(d, s, r, vk);
 }
 
 }  // namespace

@@ -51,8 +51,16 @@ struct Resolved {
   // Bezier TransformInput (base/adaptors.rs:137-139)
   int32_t has_transform = 0;
   double in_add = 0, in_mul = 1;
-  // every de Boor denominator reachable from [lo, hi] is a non-zero power of two
-  int32_t pow2_denominators = 0;
+  // span-row table of the fast B-spline kernel (rows.cuh / rows_layout.hpp); rows_mode 0 = none,
+  // 1 = every reachable denominator is a power of two (exact inverse multiply), 2 = exact division
+  // from tabulated reciprocals.
+  int32_t rows_mode = 0;
+  uint32_t rows_n = 0, rows_lo = 0, rows_len = 0;
+  std::vector<unsigned char> rows;
+  // equidistant span division (x - offset) / step: 0 IEEE divide, 1 exact inverse multiply, 2 exact
+  // division from eq_rstep = RN(1 / step)
+  int32_t eq_mode = 0;
+  double eq_rstep = 0;
 };
 
 // Validates up to and including `stage`; fills `err` like the reference's error structs.

@@ -1,0 +1,82 @@
+// Layout of the span-row table shared by the host builder (resolve.cpp) and the kernel (rows.cuh).
+#pragma once
+#if defined(__CUDACC__)
+#define ENTERP_HD __host__ __device__
+#else
+#define ENTERP_HD
+#endif
+
+namespace enterp {
+
+constexpr int ROWS_MAX_DEGREE = 7;
+constexpr unsigned ROWS_MAX_BYTES = 64u * 1024u;  // shared-memory budget of the row table per CTA
+
+// ---- compile-time schedule of the factor computations ------------------------------------------
+// Factors f(r, j), r = 1..P, j = 0..P-r, use numerator index m = j + r - 1 and denominator
+// kn[P + j] - kn[m]. With W lanes per operation, neighbours (j, j+1) of one r share an operation;
+// the leftover factor of every r with an odd count always has m = P - 1, and leftovers are paired
+// with each other (a last unpaired lane duplicates its neighbour).
+struct FactorSched {
+  int nops;
+  int r[28][2];
+  int j[28][2];
+};
+
+ENTERP_HD constexpr FactorSched make_sched(int P, int W) {
+  FactorSched s{};
+  int n = 0;
+  if (W == 1) {
+    for (int r = 1; r <= P; ++r)
+      for (int j = 0; j + r <= P; ++j) {
+        s.r[n][0] = r; s.j[n][0] = j; s.r[n][1] = r; s.j[n][1] = j;
+        ++n;
+      }
+    s.nops = n;
+    return s;
+  }
+  int sr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int ns = 0;
+  for (int r = 1; r <= P; ++r) {
+    const int cnt = P - r + 1;
+    for (int j = 0; j + 1 < cnt; j += 2) {
+      s.r[n][0] = r; s.j[n][0] = j; s.r[n][1] = r; s.j[n][1] = j + 1;
+      ++n;
+    }
+    if (cnt % 2) sr[ns++] = r;
+  }
+  for (int k = 0; k < ns; k += 2) {
+    const int r0 = sr[k], r1 = (k + 1 < ns) ? sr[k + 1] : sr[k];
+    s.r[n][0] = r0; s.j[n][0] = P - r0; s.r[n][1] = r1; s.j[n][1] = P - r1;
+    ++n;
+  }
+  s.nops = n;
+  return s;
+}
+
+ENTERP_HD constexpr int sched_nops(int P, int W) { return make_sched(P, W).nops; }
+// operation / lane that produces factor (r, j)
+ENTERP_HD constexpr int sched_find(int P, int W, int r, int j) {
+  const FactorSched s = make_sched(P, W);
+  for (int t = 0; t < s.nops; ++t)
+    for (int l = 0; l < W; ++l)
+      if (s.r[t][l] == r && s.j[t][l] == j) return t * 2 + l;
+  return -1;
+}
+
+// Row layout in units of R (shared by host builder and kernel):
+//   [0,            NOPS*W)  left knots kl           (lane-major inside an op)
+//   [NOPS*W,     2*NOPS*W)  y = RN(1/den)  (POW2 rows: the exact inverse)
+//   [2*NOPS*W,   3*NOPS*W)  -den
+//   [3*NOPS*W, 3*NOPS*W + (P+1)*DHP)  elements, each padded to DHP = roundup(DH, W) components
+//   padded to a multiple of 16 bytes.
+template <class R>
+ENTERP_HD constexpr int lanes_of() { return sizeof(R) == 4 ? 2 : 1; }
+ENTERP_HD constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+template <class R>
+ENTERP_HD constexpr int row_len(int P, int DH) {
+  const int W = lanes_of<R>();
+  return round_up(3 * sched_nops(P, W) * W + (P + 1) * round_up(DH, W), 16 / (int)sizeof(R));
+}
+
+
+}  // namespace enterp
