@@ -213,8 +213,12 @@ enterp_status dispatch_eval(const Resolved& r, const Replica& rp, const SampleSr
     case ENTERP_BSPLINE: {
       if (r.degree > (uint64_t)MAX_DYN_DEGREE) return ENTERP_UNSUPPORTED;
       const int deg = r.degree <= 7 ? (int)r.degree : 0;
-      if (r.rows_mode && rp.rows && deg > 0 && !g_disable_rows) {
-        // fast path: per-span rows staged in shared memory by TMA (rows.cuh)
+      // Span-row fast path (rows.cuh). Preconditions checked here: 16-byte aligned output, no reachable
+      // map_from special case (adaptors.rs:31-39 needs inner == 0 or inner == inner_len), and for
+      // equidistant knots a span division the kernel can do exactly without the IEEE divide.
+      const bool map_simple = (r.imin > 0 && r.imax < r.inner_len) || r.adaptor == AD_NONE;
+      const bool eq_ok = !equi || (r.rows_mode == 1 ? r.eq_mode == 1 : r.eq_mode >= 1);
+      if (r.rows_mode && rp.rows && deg > 0 && vec_ok && map_simple && eq_ok && !g_disable_rows) {
         RowsDev<R> rw{};
         rw.table = static_cast<const R*>(rp.rows);
         rw.n_rows = r.rows_n;
@@ -222,7 +226,7 @@ enterp_status dispatch_eval(const Resolved& r, const Replica& rp, const SampleSr
         rw.bytes = (uint32_t)r.rows.size();
         rw.one = R(1);
         rw.eq_rstep = (R)r.eq_rstep;
-        rw.eq_mode = r.eq_mode;
+        rw.ri_off = (uint32_t)((int64_t)r.map_add - (int64_t)r.rows_lo);
         e = launch_bspline_rows<R>(r.dh, proj, deg, equi, r.rows_mode == 1, d, s, static_cast<R*>(out), vec_ok, rw, st);
       } else {
         e = launch_bspline<R>(r.dh, proj, deg, equi, d, s, static_cast<R*>(out), vec_ok, st);

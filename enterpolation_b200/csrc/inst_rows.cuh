@@ -20,10 +20,10 @@ cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, rw.bytes) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  unsigned long long want = (s.count + BLOCK - 1) / BLOCK;
+  unsigned long long want = (s.count + ROWS_S * BLOCK - 1) / (ROWS_S * BLOCK);
   const unsigned long long cap = (unsigned long long)per_sm * (unsigned long long)sm_count();
   const int grid = (int)(want < cap ? want : cap);
-  kernel<<<grid, BLOCK, rw.bytes, st>>>(c, s, out, vec_ok, rw);
+  kernel<<<grid, BLOCK, rw.bytes, st>>>(c, s, out, rw);
   count_launch();
   return cudaGetLastError();
 }

@@ -49,7 +49,7 @@ struct RowsDev {
   uint32_t bytes;     // n_rows * row_len * sizeof(R), multiple of 16
   R one;              // 1.0, opaque to the compiler (see header comment)
   R eq_rstep;         // RN(1 / eq_step) (exact when eq_step is a power of two)
-  int eq_mode;        // equidistant span division: 0 IEEE div, 1 exact inverse multiply, 2 Markstein
+  uint32_t ri_off;    // row index = inner index + ri_off (mod 2^32): map_add - lo
 };
 
 // ---- exact arithmetic -------------------------------------------------------------------------

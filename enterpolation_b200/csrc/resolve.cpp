@@ -270,9 +270,11 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
     for (int i = 0; i <= p; ++i)
       for (int c = 0; c < r.dh; ++c) row[3 * nops * W + i * dhp + c] = el[(idx - p + i) * r.dh + c];
   }
-  if (all_pow2)
+  // mode 1 multiplies by exact inverses everywhere (the equidistant span division included), mode 2
+  // divides exactly from tabulated reciprocals; both need the span division to be covered.
+  if (all_pow2 && (!equi || r.eq_mode == 1))
     r.rows_mode = 1;
-  else if (all_window)
+  else if (all_window && (!equi || r.eq_mode >= 1))
     r.rows_mode = 2;
   else
     return;

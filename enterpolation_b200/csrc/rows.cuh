@@ -129,32 +129,6 @@ __device__ __forceinline__ bool in_guard(R a) {
   return (m >= PK<R>::guard_lo()) && (m <= PK<R>::guard_hi());
 }
 
-// Equidistant::strict_upper_bound_clamped with the division replaced by its exact equivalent.
-template <class R>
-__device__ __forceinline__ bool equi_inner_index_fast(const CurveDev<R>& c, const RowsDev<R>& rw, R x, uint32_t& idx) {
-  if (x < c.eq_first) {
-    idx = c.imin;
-    return true;
-  }
-  const R num = xsub(x, c.eq_offset);
-  R scaled;
-  if (rw.eq_mode == 1) {
-    scaled = xmul(num, rw.eq_rstep);
-  } else if (rw.eq_mode == 2 && in_guard(num)) {
-    scaled = exact_div_scalar<R>(num, rw.eq_rstep, -c.eq_step);
-  } else {
-    scaled = xdiv(num, c.eq_step);
-  }
-  if (!to_usize_ok(scaled)) return false;
-  if (scaled >= R(4294967040.0)) {
-    idx = c.imax;
-  } else {
-    const uint32_t u = (uint32_t)scaled;  // truncation == floor for scaled >= 0
-    idx = u >= c.imax ? c.imax : u + 1u;
-  }
-  return true;
-}
-
 // ---- TMA bulk staging ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -184,10 +158,51 @@ __device__ __forceinline__ void stage_rows(void* smem_dst, const void* gmem_src,
 }
 
 // =================================================================================================
-template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2>
-__global__ void __launch_bounds__(BLOCK) bspline_rows_kernel(const CurveDev<R> c, const SampleSrc<R> s,
-                                                             R* __restrict__ out, const bool vec_ok,
-                                                             const RowsDev<R> rw) {
+// Branch-light equidistant span (Equidistant::strict_upper_bound_clamped, list.rs:476-488) returning
+// the ROW index directly: ri = map_from(inner) - lo = inner + ri_off when neither map_from special
+// case (inner == 0, inner == inner_len) can occur (host flag rw.map_simple).
+template <class R>
+__device__ __forceinline__ uint32_t sat_u32(R v);
+template <>
+__device__ __forceinline__ uint32_t sat_u32<float>(float v) { return __float2uint_rz(v); }   // saturating, NaN -> 0
+template <>
+__device__ __forceinline__ uint32_t sat_u32<double>(double v) { return __double2uint_rz(v); }
+
+// The host only selects this kernel when (resolve.cpp / capi.cu):
+//   * map_from(inner) has no reachable special case, so the row index is inner + ri_off;
+//   * EQUI: eq_step is a power of two for POW2 rows (scaled = num * (1/step) exactly), and within the
+//     safe window otherwise (exact division from eq_rstep = RN(1/step), IEEE fallback off-window).
+template <class R, bool EQUI, bool POW2>
+__device__ __forceinline__ uint32_t rows_span(const CurveDev<R>& c, const RowsDev<R>& rw, R x, bool& valid) {
+  uint32_t inner;
+  if (EQUI) {
+    const R num = xsub(x, c.eq_offset);
+    R scaled;
+    if (POW2) {
+      scaled = xmul(num, rw.eq_rstep);
+    } else if (in_guard(num)) {
+      scaled = exact_div_scalar<R>(num, rw.eq_rstep, -c.eq_step);
+    } else {
+      scaled = xdiv(num, c.eq_step);
+    }
+    const bool left = x < c.eq_first;
+    // floor(scaled).to_usize().unwrap() panics unless 0 <= scaled < 2^64 (NaN fails both tests)
+    valid = left || ((scaled >= R(0)) && (scaled < R(18446744073709551616.0)));
+    const uint32_t u = sat_u32<R>(scaled);              // trunc == floor for scaled >= 0
+    const uint32_t up = min(u, c.imax - 1u) + 1u;        // min(imax, floor + 1); imax >= 1
+    inner = (left || !valid) ? c.imin : up;
+  } else {
+    valid = true;
+    inner = c.imin + coop_count_le(c, x);
+  }
+  return min(inner + rw.ri_off, rw.n_rows - 1u);  // the clamp is a no-op for every valid sample
+}
+
+constexpr int ROWS_S = 2;  // samples per thread per loop trip (block-strided, so stores stay coalesced)
+
+template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, bool TAKE>
+__device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<R>& s, R* __restrict__ out,
+                                          const RowsDev<R>& rw, const R* __restrict__ tab) {
   using P = PK<R>;
   using T = typename P::T;
   constexpr int W = P::W;
@@ -196,42 +211,33 @@ __global__ void __launch_bounds__(BLOCK) bspline_rows_kernel(const CurveDev<R> c
   constexpr int ROW = row_len<R>(DEG, DH);
   constexpr int VEC = 16 / (int)sizeof(R);  // R values per 128-bit shared load
   constexpr int EL0 = 3 * NOPS * W;
+  constexpr int D = PROJ ? DH - 1 : DH;
+  constexpr unsigned long long TILE = (unsigned long long)ROWS_S * BLOCK;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long mbar;
-  stage_rows(smem_raw, rw.table, rw.bytes, &mbar);
-  const R* __restrict__ tab = reinterpret_cast<const R*>(smem_raw);
+  const unsigned long long stride = (unsigned long long)gridDim.x * TILE;
+  const unsigned long long block0 = (unsigned long long)blockIdx.x * TILE;
+  if (block0 >= s.count) return;
+  const unsigned long long rest = s.count - block0;
+  // trips in which the whole tile is in range need no bounds checks; at most one ragged trip follows
+  const uint32_t n_full = rest >= TILE ? (uint32_t)((rest - TILE) / stride) + 1u : 0u;
+  const uint32_t n_trips = (uint32_t)((rest + stride - 1) / stride);
+  const unsigned long long i0 = block0 + threadIdx.x;
+  unsigned long long gi = s.first + i0;  // global stepper index of this thread's first sample (take mode)
+  const R* __restrict__ tp = TAKE ? nullptr : s.t + i0;
+  R* __restrict__ op = out + i0 * D;
 
   R row[ROW];
   uint32_t cached = 0xFFFFFFFFu;
   const T one2 = P::bcast(rw.one);
 
-  for (unsigned long long base = (unsigned long long)blockIdx.x * BLOCK; base < s.count;
-       base += (unsigned long long)gridDim.x * BLOCK) {
-    const unsigned long long i = base + threadIdx.x;
-    const bool active = i < s.count;
-    const R x = active ? sample_param(s, i) : c.eq_first;
-    uint32_t index;
-    bool valid = true;
-    if (EQUI) {
-      uint32_t inner;
-      valid = equi_inner_index_fast(c, rw, x, inner);
-      if (!valid) inner = c.imin;
-      index = map_from_inner(c, inner);
-    } else {
-      index = map_from_inner(c, c.imin + coop_count_le(c, x));
-    }
-    if (!active) continue;
-    const uint32_t ri = index - rw.lo;
+  // de Boor for one sample whose span row index is ri (bspline/mod.rs:156-168)
+  auto eval_one = [&](const R x, const bool valid, const uint32_t ri, R* __restrict__ dst) {
     if (ri != cached) {
       const float4* __restrict__ src = reinterpret_cast<const float4*>(tab + (size_t)ri * ROW);
 #pragma unroll
-      for (int k = 0; k < ROW / VEC; ++k) {
-        unpack128(src[k], &row[k * VEC]);
-      }
+      for (int q = 0; q < ROW / VEC; ++q) unpack128(src[q], &row[q * VEC]);
       cached = ri;
     }
-    // ---- factors -------------------------------------------------------------------------------
     T fac[NOPS], omf[NOPS];
     bool fast_ok = true;
 #pragma unroll
@@ -264,7 +270,6 @@ __global__ void __launch_bounds__(BLOCK) bspline_rows_kernel(const CurveDev<R> c
 #pragma unroll
     for (int t = 0; t < NOPS; ++t) omf[t] = P::sub(one2, fac[t]);
 
-    // ---- de Boor triangle ------------------------------------------------------------------------
     R ws[DEG * DHP];  // levels r >= 1 (level 0 is read straight from the cached row)
     static_for<1, DEG + 1>([&](auto rc) {
       constexpr int r = decltype(rc)::value;
@@ -279,22 +284,81 @@ __global__ void __launch_bounds__(BLOCK) bspline_rows_kernel(const CurveDev<R> c
         R* o = &ws[j * DHP];
         if constexpr (W == 2) {
 #pragma unroll
-          for (int k = 0; k + 1 < DH; k += 2) {
-            const T t1 = P::mul(P::make(a[k], a[k + 1]), P::bcast(om));
-            const T t2 = P::mul(P::make(b[k], b[k + 1]), P::bcast(f));
+          for (int q = 0; q + 1 < DH; q += 2) {
+            const T t1 = P::mul(P::make(a[q], a[q + 1]), P::bcast(om));
+            const T t2 = P::mul(P::make(b[q], b[q + 1]), P::bcast(f));
             const T v = P::fma(t1, one2, t2);
-            o[k] = P::lane(v, 0);
-            o[k + 1] = P::lane(v, 1);
+            o[q] = P::lane(v, 0);
+            o[q + 1] = P::lane(v, 1);
           }
           if (DH % 2) o[DH - 1] = merge1(a[DH - 1], b[DH - 1], f, om);
         } else {
 #pragma unroll
-          for (int k = 0; k < DH; ++k) o[k] = merge1(a[k], b[k], f, om);
+          for (int q = 0; q < DH; ++q) o[q] = merge1(a[q], b[q], f, om);
         }
       });
     });
-    finish_and_store<R, DH, PROJ>(out, i, ws, valid, vec_ok, c.invalid);
+    // project + store (dst is 16-byte aligned on this path; the host checks)
+    R v[D];
+    if (PROJ) {
+      const R rat = ws[DH - 1];  // Homogeneous::project (weights/homogeneous.rs:134-136)
+#pragma unroll
+      for (int q = 0; q < D; ++q) v[q] = xdiv(ws[q], rat);
+    } else {
+#pragma unroll
+      for (int q = 0; q < D; ++q) v[q] = ws[q];
+    }
+    if (!valid) {
+#pragma unroll
+      for (int q = 0; q < D; ++q) v[q] = qnan(R(0));
+      atomicAdd(c.invalid, 1ull);
+    }
+    store_elem<R, D>(dst, 0, v, true);
+  };
+
+  auto param = [&](const int slot, const bool active) -> R {
+    if (TAKE) return xadd(xmul(s.step, from_index(gi + (unsigned long long)slot * BLOCK, R(0))), s.start);
+    return active ? __ldcs(tp + slot * BLOCK) : c.eq_first;
+  };
+
+  uint32_t k = 0;
+  for (; k < n_full; ++k, gi += stride, op += stride * D) {
+    R x[ROWS_S];
+    bool valid[ROWS_S];
+    uint32_t ri[ROWS_S];
+#pragma unroll
+    for (int u = 0; u < ROWS_S; ++u) {
+      x[u] = param(u, true);
+      ri[u] = rows_span<R, EQUI, POW2>(c, rw, x[u], valid[u]);
+    }
+    if (!TAKE) tp += stride;
+#pragma unroll
+    for (int u = 0; u < ROWS_S; ++u) eval_one(x[u], valid[u], ri[u], op + (size_t)u * BLOCK * D);
   }
+  if (k < n_trips) {  // ragged last tile of the launch
+    const unsigned long long here = i0 + (unsigned long long)k * stride;
+#pragma unroll 1
+    for (int u = 0; u < ROWS_S; ++u) {
+      const bool active = here + (unsigned long long)u * BLOCK < s.count;
+      const R x = param(u, active);
+      bool valid;
+      const uint32_t ri = rows_span<R, EQUI, POW2>(c, rw, x, valid);
+      if (active) eval_one(x, valid, ri, op + (size_t)u * BLOCK * D);
+    }
+  }
+}
+
+template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2>
+__global__ void __launch_bounds__(BLOCK) bspline_rows_kernel(const CurveDev<R> c, const SampleSrc<R> s,
+                                                             R* __restrict__ out, const RowsDev<R> rw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar;
+  stage_rows(smem_raw, rw.table, rw.bytes, &mbar);
+  const R* __restrict__ tab = reinterpret_cast<const R*>(smem_raw);
+  if (s.t)
+    rows_body<R, DH, PROJ, DEG, EQUI, POW2, false>(c, s, out, rw, tab);
+  else
+    rows_body<R, DH, PROJ, DEG, EQUI, POW2, true>(c, s, out, rw, tab);
 }
 
 }  // namespace enterp
