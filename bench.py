@@ -6,8 +6,10 @@ Headline workload (BASELINE.json configs[4], the one north_star's target is quot
       shape, 5 stops), `take(2^32)`; the GLOBAL sample range is sharded contiguously over the N
       ranks (strong scaling: total work fixed; no collective on the data path).
 A step = one pass of the hot path over a rank's whole shard (one kernel launch).
+The other BASELINE.json configs (C1-C4) are timed briefly as well and reported under "configs" in
+the same JSON line (skip with --no-extra).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--log2-samples 32] [--stops 5] [--extra]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--log2-samples 32] [--stops 5] [--no-extra]
   python bench.py --impl reference ...      # the CPU oracle (restatement of the reference) on host cores
 """
 from __future__ import annotations
@@ -27,30 +29,295 @@ if ROOT not in sys.path:
 
 METRIC = "curve samples/sec"
 UNIT = "samples/s"
-BYTES_PER_SAMPLE = 16  # [f32;4] store only: t is generated on the device
+
+# FP-pipe issue peaks measured on this pool's B200 with tools/pipebench.cu (profiles/r01_pipebench.json):
+# dependency-free unfused FMUL/FADD chains, whole chip, lane-operations per second.
+FP32_LANE_OPS = 3.45e13
+FP64_LANE_OPS = 1.80e13
 
 
-def u01_f32(n, seed):
-    idx = np.arange(n, dtype=np.uint64)
+# ---- deterministic synthetic inputs: splitmix64(seed + index) ----------------------
+def splitmix64(idx, seed):
     with np.errstate(over="ignore"):
-        z = idx + np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15)
+        z = idx.astype(np.uint64) + np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         z = z ^ (z >> np.uint64(31))
-    return ((z >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+    return z
+
+
+def u01(n, seed, dtype, offset=0):
+    z = splitmix64(np.arange(offset, offset + n, dtype=np.uint64), seed)
+    if dtype == np.float32:
+        return ((z >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+    return (z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+
+def u01_torch(n, seed, dtype, device, offset=0):
+    """Same generator on the GPU (int64 arithmetic wraps like uint64; logical shifts are masked)."""
+    import torch
+
+    def lsr(z, k):
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    def c(v):  # uint64 constant as a wrapped int64
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    out = torch.empty(n, dtype=dtype, device=device)
+    chunk = 1 << 26
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        z = torch.arange(offset + lo, offset + lo + m, dtype=torch.int64, device=device) + c(seed) + c(0x9E3779B97F4A7C15)
+        z = (z ^ lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
+        z = z ^ lsr(z, 31)
+        if dtype == torch.float32:
+            out[lo:lo + m] = lsr(z, 40).to(torch.float32) * (2.0 ** -24)
+        else:
+            out[lo:lo + m] = lsr(z, 11).to(torch.float64) * (2.0 ** -53)
+    return out
+
+
+# ---- workloads ------------------------------------------------------------------------------------
+class Workload:
+    """One BASELINE.json config, sharded for (rank, world). Subclasses build device state in setup()."""
+    key = ""
+    name = ""
+    dtype = "f32"
+    kernel = ""
+    bytes_per_sample = 0      # algorithmic HBM bytes per sample (SURVEY.md §8d)
+    fp_ops_per_sample = 0     # exact-order FP operations per sample, div = 1 (SURVEY.md §8a)
+    fp_peak = FP32_LANE_OPS
+
+    def __init__(self, rank=0, world=1, device=0):
+        self.rank, self.world, self.device = rank, world, device
+        self.samples = 0         # samples this rank evaluates per step
+        self.samples_total = 0   # whole job
+
+    def setup(self):
+        raise NotImplementedError
+
+    def step(self):
+        raise NotImplementedError
+
+    def cpu_rate(self, threads, n):
+        """samples/s of the CPU oracle on a bounded sample of this workload."""
+        raise NotImplementedError
 
 
 def gradient_builder(stops: int):
     from enterpolation_b200 import BSpline
-    el = u01_f32(stops * 4, 0xE1).reshape(stops, 4)
+    el = u01(stops * 4, 0xE1, np.float32).reshape(stops, 4)
     return BSpline.builder().clamped().elements(el).equidistant("f32").degree(3).normalized().dynamic()
 
 
-def workload_name(log2n, stops):
-    return (f"C5 dynamic clamped equidistant cubic BSpline [f32;4], {stops} stops, take(2^{log2n}) "
-            f"sharded over ranks by contiguous global sample range")
+class TakeWorkload(Workload):
+    """take(n_total) of one curve, global sample range sharded contiguously (C1, C5)."""
+
+    def __init__(self, builder, log2n, dim, torch_dtype, **kw):
+        super().__init__(**kw)
+        self.builder, self.log2n, self.dim, self.torch_dtype = builder, log2n, dim, torch_dtype
+
+    def setup(self):
+        import torch
+        from enterpolation_b200 import shard_range
+        self.n_total = 1 << self.log2n
+        self.samples_total = self.n_total
+        self.lo, hi = shard_range(self.n_total, self.rank, self.world)
+        self.samples = hi - self.lo
+        self.curve = self.builder.on_device(self.device).build()
+        self.curve.upload(self.device)
+        shape = (self.samples, self.dim) if self.dim > 1 else (self.samples,)
+        self.out = torch.empty(shape, dtype=self.torch_dtype, device=f"cuda:{self.device}")
+        return self
+
+    def step(self):
+        self.curve.take_device(self.n_total, self.lo, self.samples, out=self.out, device=self.device)
+
+    def cpu_rate(self, threads, n):
+        from oracle import oracle
+        ref = oracle.OracleCurve(self.builder.to_desc())
+        n = min(n, self.n_total)
+        first = (self.n_total - n) // 2
+        t0 = time.perf_counter()
+        ref.take(self.n_total, first, n, threads=threads)
+        return n / (time.perf_counter() - t0)
 
 
+class C5(TakeWorkload):
+    key = "C5"
+    kernel = "bspline_rows_kernel<float,4,false,3,true,POW2>"
+    bytes_per_sample = 16
+    fp_ops_per_sample = 125
+
+    def __init__(self, log2n=32, stops=5, **kw):
+        import torch
+        super().__init__(gradient_builder(stops), log2n, 4, torch.float32, **kw)
+        self.stops = stops
+        self.name = (f"C5 dynamic clamped equidistant cubic BSpline [f32;4], {stops} stops, take(2^{log2n}) "
+                     f"sharded over ranks by contiguous global sample range")
+
+
+class C1(TakeWorkload):
+    key = "C1"
+    dtype = "f64"
+    kernel = "bspline_rows_kernel<double,1,false,3,true,false>"
+    bytes_per_sample = 8
+    fp_ops_per_sample = 71
+    fp_peak = FP64_LANE_OPS
+
+    def __init__(self, log2n=24, **kw):
+        import torch
+        from enterpolation_b200 import BSpline
+        b = (BSpline.builder().clamped().elements([0.0, 0.0, 0.0, 6.0, 0.0, 0.0, 0.0]).equidistant("f64").degree(3)
+             .domain(-2.0, 2.0).constant(4))
+        super().__init__(b, log2n, 1, torch.float64, **kw)
+        self.name = f"C1 README cardinal cubic clamped BSpline, 7 f64 elements, equidistant knots on [-2,2], take(2^{log2n})"
+
+
+class BatchWorkload(Workload):
+    """sample(t) over a device-resident batch of parameters, batch sharded contiguously (C2, C4)."""
+
+    def make(self):
+        """-> (builder, n_total, dim, np dtype, torch dtype, seed_t)"""
+        raise NotImplementedError
+
+    def setup(self):
+        import torch
+        from enterpolation_b200 import shard_range
+        self.builder, self.n_total, self.dim, npdt, tdt = self.make()
+        self.samples_total = self.n_total
+        lo, hi = shard_range(self.n_total, self.rank, self.world)
+        self.lo, self.samples = lo, hi - lo
+        self.curve = self.builder.on_device(self.device).build()
+        self.curve.upload(self.device)
+        d = self.curve.domain()
+        dev = f"cuda:{self.device}"
+        u = u01_torch(self.samples, 0xE4, tdt, dev, offset=lo)
+        self.t = (float(d[0]) + u * (float(d[1]) - float(d[0]))).to(tdt).contiguous()
+        self.out = torch.empty((self.samples, self.dim), dtype=tdt, device=dev)
+        self.npdt = npdt
+        return self
+
+    def step(self):
+        self.curve.sample_device(self.t, out=self.out)
+
+    def cpu_rate(self, threads, n):
+        from oracle import oracle
+        ref = oracle.OracleCurve(self.builder.to_desc())
+        n = min(n, self.samples)
+        t = self.t[:n].cpu().numpy()
+        t0 = time.perf_counter()
+        ref.eval(t, threads=threads)
+        return n / (time.perf_counter() - t0)
+
+
+class C2(BatchWorkload):
+    key = "C2"
+    kernel = "linear_kernel<float,3,false,false>"
+    bytes_per_sample = 16
+    fp_ops_per_sample = 13
+
+    def __init__(self, log2n=28, log2_knots=20, **kw):
+        super().__init__(**kw)
+        self.log2n, self.log2k = log2n, log2_knots
+        self.name = (f"C2 Linear [f32;3], 2^{log2_knots} sorted non-uniform knots, 2^{log2n} random sample parameters "
+                     f"(device resident)")
+
+    def make(self):
+        import torch
+        from enterpolation_b200 import Linear
+        k = 1 << self.log2k
+        inc = 0.5 + u01(k - 1, 0xE2, np.float64)
+        knots = np.concatenate([[0.0], np.cumsum(inc)]).astype(np.float32)
+        el = (u01(k * 3, 0xE1, np.float32) * np.float32(2) - np.float32(1)).reshape(k, 3)
+        return Linear.builder().elements(el).knots(knots), 1 << self.log2n, 3, np.float32, torch.float32
+
+
+class C4(BatchWorkload):
+    key = "C4"
+    dtype = "f64"
+    kernel = "bspline_kernel<double,4,true,3,false>"
+    bytes_per_sample = 32
+    fp_ops_per_sample = 111
+    fp_peak = FP64_LANE_OPS
+
+    def __init__(self, log2n=26, log2_ctrl=16, **kw):
+        super().__init__(**kw)
+        self.log2n, self.log2c = log2n, log2_ctrl
+        self.name = (f"C4 NURBS (Weighted BSpline) degree 3 [f64;3] + weights, 2^{log2_ctrl} control points, "
+                     f"non-uniform knots, 2^{log2n} random sample parameters (device resident)")
+
+    def make(self):
+        import torch
+        from enterpolation_b200 import BSpline
+        e = 1 << self.log2c
+        pts = (u01(e * 3, 0xE1, np.float64) * 2.0 - 1.0).reshape(e, 3)
+        w = 0.5 + u01(e, 0xE3, np.float64)
+        inner = np.cumsum(0.5 + u01(e - 3, 0xE2, np.float64))  # e + 2 knots: 3 x 0, e - 4 interior, last x 3
+        knots = np.concatenate([[0.0, 0.0, 0.0], inner[:-1], [inner[-1]] * 3])
+        assert knots.shape[0] == e + 2
+        b = BSpline.builder().elements_with_weights(pts, w).knots(knots).constant(4)
+        return b, 1 << self.log2n, 3, np.float64, torch.float64
+
+
+class C3(Workload):
+    key = "C3"
+    kernel = "bezier_many_kernel<float,3,16>"
+    bytes_per_sample = 12.75
+    fp_ops_per_sample = 1081
+
+    def __init__(self, log2_curves=20, n_ctrl=16, samples=256, **kw):
+        super().__init__(**kw)
+        self.log2c, self.n_ctrl, self.per_curve = log2_curves, n_ctrl, samples
+        self.name = (f"C3 Bezier degree {n_ctrl - 1} [f32;3], 2^{log2_curves} independent curves x take({samples}) "
+                     f"(control points device resident)")
+
+    def setup(self):
+        import torch
+        from enterpolation_b200 import shard_range
+        n_curves = 1 << self.log2c
+        lo, hi = shard_range(n_curves, self.rank, self.world)
+        self.curves = hi - lo
+        self.samples = self.curves * self.per_curve
+        self.samples_total = n_curves * self.per_curve
+        dev = f"cuda:{self.device}"
+        per = self.n_ctrl * 3
+        u = u01_torch(self.curves * per, 0xE1, torch.float32, dev, offset=lo * per)
+        self.ctrl = (u * 2.0 - 1.0).reshape(self.curves, self.n_ctrl, 3).contiguous()
+        self.out = torch.empty((self.curves, self.per_curve, 3), dtype=torch.float32, device=dev)
+        return self
+
+    def step(self):
+        from enterpolation_b200 import bezier_many_take
+        bezier_many_take(self.ctrl, self.per_curve, out=self.out)
+
+    def cpu_rate(self, threads, n):
+        from oracle import oracle
+        curves = max(threads, min(self.curves, n // self.per_curve))
+        ctrl = self.ctrl[:curves].cpu().numpy()
+        t0 = time.perf_counter()
+        oracle.bezier_many_take(ctrl, self.per_curve, threads=threads)
+        return curves * self.per_curve / (time.perf_counter() - t0)
+
+
+def make_workload(case, log2n=None, arg=None, rank=0, world=1, device=0):
+    case = case.lower()
+    kw = dict(rank=rank, world=world, device=device)
+    if case == "c5":
+        return C5(log2n or 32, arg or 5, **kw).setup()
+    if case == "c1":
+        return C1(log2n or 24, **kw).setup()
+    if case == "c2":
+        return C2(log2n or 28, arg or 20, **kw).setup()
+    if case == "c3":
+        return C3(log2n or 20, arg or 16, **kw).setup()
+    if case == "c4":
+        return C4(log2n or 26, arg or 16, **kw).setup()
+    raise ValueError(case)
+
+
+# ---- clocks -----------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -113,20 +380,10 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(builder, n_total, first, count, threads):
-    """Times the CPU oracle (restatement of enterpolation 0.3.0, see oracle/) on `count` samples."""
-    from oracle import oracle
-    ref = oracle.OracleCurve(builder.to_desc())
-    t0 = time.perf_counter()
-    ref.take(n_total, first, count, threads=threads)
-    dt = time.perf_counter() - t0
-    return count / dt
-
-
+# ---- the reference arm --------------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the reference's CPU path (C++ restatement; the Rust crate cannot be built here:
-    no cargo/rustc in the image) with all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU path (C++ restatement in oracle/; the Rust crate cannot be
+    built here: no cargo/rustc in the image) with all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -148,7 +405,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.log2_samples, args.stops),
+        "config": {"workload": C5(args.log2_samples, args.stops).name,
                    "reference": "C++ restatement of enterpolation 0.3.0 eval (oracle/; Rust toolchain unavailable)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{count} consecutive samples from the middle of the 2^{args.log2_samples} take, per step"},
@@ -158,7 +415,24 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------
+# ---- our arm ------------------------------------------------------------------------------------------
+def time_steps(w, steps, warmup, stream, barrier):
+    import torch
+    for _ in range(warmup):
+        w.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        w.step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -171,6 +445,7 @@ def run_gpu(args):
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -179,52 +454,50 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
 
+    def reduce_max(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     lib = _abi.load_library()
-    builder = gradient_builder(args.stops)
-    curve = builder.on_device(local).build()
-    curve.upload(local)
-    n_total = 1 << args.log2_samples
-    lo, hi = shard_range(n_total, rank, world)
-    count = hi - lo
-    out = torch.empty((count, 4), dtype=torch.float32, device=f"cuda:{local}")
     stream = torch.cuda.current_stream(local)
+    peaks, how = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    cores = os.cpu_count() or 1
+    warmup = max(args.warmup, 3)
 
-    def step():
-        curve.take_device(n_total, lo, count, out=out, device=local)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
+    # ---- headline: C5 ---------------------------------------------------------------------------
+    w = C5(args.log2_samples, args.stops, rank=rank, world=world, device=local).setup()
+    for _ in range(warmup):
+        w.step()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.enterp_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = time_steps(w, args.steps, 0, stream, barrier)
     launches = lib.enterp_launch_count() - launches0
     clocks = sampler.finish()
-    tms = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-    tl = torch.tensor([launches], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
-    ms_max = float(tms.item())
-    value = n_total * args.steps / (ms_max * 1e-3)
+    ms_max = reduce_max(ms)
+    total_launches = int(reduce_sum(launches))
+    value = w.samples_total * args.steps / (ms_max * 1e-3)
 
     # ---- e2e: the user-facing call with HOST buffers (build + take(n).collect() of a window) -------
-    e2e_count_total = min(n_total, 1 << args.log2_e2e)
-    e_lo, e_hi = shard_range(e2e_count_total, rank, world)
-    e_first = (n_total - e2e_count_total) // 2 + e_lo
+    n_total = w.n_total
+    e2e_total = min(n_total, 1 << args.log2_e2e)
+    e_lo, e_hi = shard_range(e2e_total, rank, world)
+    e_first = (n_total - e2e_total) // 2 + e_lo
     e_count = e_hi - e_lo
     host = torch.empty((e_count, 4), dtype=torch.float32, pin_memory=True)
+    host.zero_()  # touch the pinned pages before timing
     table_bytes = args.stops * 16 + (args.stops + 2) * 4
+    builder = w.builder
 
     def e2e_step():
         c = builder.on_device(local).build()  # builder validation + table upload inside the timed region
@@ -232,7 +505,7 @@ def run_gpu(args):
         assert st == 0, st
         return float(host[-1, 0])  # the device->host result is read
 
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
@@ -240,46 +513,78 @@ def run_gpu(args):
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tdt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_count_total * e2e_steps / float(tdt.item())
+    e2e_dt = reduce_max(time.perf_counter() - t0)
+    e2e_value = e2e_total * e2e_steps / e2e_dt
+    del host
+
+    per_launch_ms = ms / args.steps  # rank 0's kernel: one launch per step
+    achieved = w.samples * w.bytes_per_sample / (per_launch_ms * 1e-3) / 1e9
+    cpu_1t = cpu_all = None
+    if rank == 0:
+        cpu_1t = w.cpu_rate(1, 1 << 22)
+        cpu_all = w.cpu_rate(cores, 1 << 25)
+    c5_samples = w.samples
+    c5_name = w.name
+    rows_kernel = w.kernel
+    del w
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configs, briefly ---------------------------------------------------
+    extra = {}
+    if not args.no_extra:
+        for cls in (C1, C2, C3, C4):
+            try:
+                x = cls(rank=rank, world=world, device=local).setup()
+                xsteps = 10
+                xms = reduce_max(time_steps(x, xsteps, 3, stream, barrier))
+                xval = x.samples_total * xsteps / (xms * 1e-3)
+                own = x.samples / (xms / xsteps * 1e-3)  # this rank's kernel
+                entry = {
+                    "workload": x.name, "value": xval, "unit": UNIT, "ms_per_step": xms / xsteps, "dtype": x.dtype,
+                    "kernel": x.kernel,
+                    "hbm": {"algorithmic_bytes_per_sample": x.bytes_per_sample,
+                            "achieved_gbs": own * x.bytes_per_sample / 1e9, "peak_gbs": hbm_peak,
+                            "frac": own * x.bytes_per_sample / 1e9 / hbm_peak},
+                    "fp_pipe": {"exact_order_fp_ops_per_sample": x.fp_ops_per_sample,
+                                "achieved_lane_ops_per_s": own * x.fp_ops_per_sample, "peak_lane_ops_per_s": x.fp_peak,
+                                "frac": own * x.fp_ops_per_sample / x.fp_peak,
+                                "peak_source": "tools/pipebench.cu unfused FMUL/FADD (DMUL/DADD) chains, profiles/r01_pipebench.json"},
+                }
+                if rank == 0:
+                    entry["cpu_baseline"] = {"single_thread": x.cpu_rate(1, 1 << 20), "all_cores": x.cpu_rate(cores, 1 << 23),
+                                             "cores": cores, "unit": UNIT, "kind": "port"}
+                extra[x.key] = entry
+                del x
+                torch.cuda.empty_cache()
+            except Exception as ex:  # an extra must never take the headline down
+                extra[cls.key] = {"error": repr(ex)}
 
     if rank == 0:
-        peaks, how = measured_peaks()
-        per_launch_ms = ms / args.steps  # rank 0's kernel: one launch per step
-        achieved = count * BYTES_PER_SAMPLE / (per_launch_ms * 1e-3) / 1e9
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        cores = os.cpu_count() or 1
-        cpu_n1 = min(n_total, 1 << 22)
-        cpu_nall = min(n_total, 1 << 25)
-        mid = (n_total - cpu_nall) // 2
-        cpu_1t = cpu_reference_rate(builder, n_total, mid, cpu_n1, 1)
-        cpu_all = cpu_reference_rate(builder, n_total, mid, cpu_nall, cores)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.log2_samples, args.stops),
-                       "samples_total": n_total, "samples_per_rank": count, "elements": f"[f32;4] x {args.stops}",
+            "config": {"workload": c5_name, "samples_total": n_total, "samples_per_rank": c5_samples,
+                       "elements": f"[f32;4] x {args.stops}",
                        "l2_policy": "outputs (16 B/sample, %.1f GiB per rank) are larger than L2; nothing is re-read"
-                                    % (count * 16 / 2 ** 30),
+                                    % (c5_samples * 16 / 2 ** 30),
                        "parity": "bit-exact vs CPU oracle (tests/test_gpu_parity.py::test_config_shapes_small)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": table_bytes,
                     "d2h_bytes_per_step": e_count * 16,
-                    "what": f"builder.build() + enterp_take_host over a {e2e_count_total}-sample window of the "
+                    "what": f"builder.build() + enterp_take_host over a {e2e_total}-sample window of the "
                             f"2^{args.log2_samples} take (pinned host buffer, chunked kernel/D2H pipeline), "
                             f"{e2e_steps} steps, wall clock max over ranks"},
-            "gpu_launches": int(tl.item()),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "bspline_kernel<float,4,false,3,true>",
-                         "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE, "peak_source": f"MEASURED_PEAKS.json ({how}, burst copy)"},
+            "gpu_launches": total_launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "kernel": rows_kernel,
+                         "algorithmic_bytes_per_sample": 16, "peak_source": f"MEASURED_PEAKS.json ({how}, burst copy)",
+                         "fp32_pipe_frac": c5_samples * 125 / (per_launch_ms * 1e-3) / FP32_LANE_OPS},
             "cpu_baseline": {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
                              "single_thread": cpu_1t,
-                             "sample": f"{cpu_nall} consecutive samples (all cores) / {cpu_n1} (1 thread) from the middle of the take; "
+                             "sample": f"{1 << 25} consecutive samples (all cores) / {1 << 22} (1 thread) from the middle of the take; "
                                        "C++ restatement of enterpolation 0.3.0 (oracle/), per-eval heap workspace as DynSpace"},
+            "configs": extra,
         }
         print(json.dumps(line), flush=True)
     barrier()
@@ -296,6 +601,7 @@ def main():
     ap.add_argument("--log2-samples", type=int, default=32)
     ap.add_argument("--log2-e2e", type=int, default=28)
     ap.add_argument("--stops", type=int, default=5)
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

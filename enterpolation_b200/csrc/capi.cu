@@ -39,6 +39,12 @@ static const bool g_disable_rows = [] {
   return v && v[0] == '1';
 }();
 
+// Ablation switch (env ENTERP_COOP_SEARCH=1): warp-cooperative ballot search instead of per-thread.
+static const bool g_coop_search = [] {
+  const char* v = std::getenv("ENTERP_COOP_SEARCH");
+  return v && v[0] == '1';
+}();
+
 static thread_local std::string t_cuda_error;
 static enterp_status cuda_fail(cudaError_t e, const char* where) {
   t_cuda_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
@@ -173,6 +179,7 @@ CurveDev<R> make_dev(const Resolved& r, const Replica& rp) {
   d.in_add = (R)r.in_add;
   d.in_mul = (R)r.in_mul;
   d.has_transform = r.has_transform;
+  d.coop_search = g_coop_search ? 1 : 0;
   d.invalid = rp.invalid;
   return d;
 }

@@ -29,6 +29,7 @@ struct CurveDev {
   R eq_step, eq_offset, eq_first, eq_lenm2;
   R in_add, in_mul;
   int has_transform;
+  int coop_search;              // ablation switch: warp-cooperative instead of per-thread pivot search
   unsigned long long* invalid;  // device counter: samples where the reference would panic
 };
 
@@ -105,9 +106,18 @@ __device__ __forceinline__ bool equi_inner_index(const CurveDev<R>& c, R x, uint
   return true;
 }
 
-// Warp-cooperative 32-ary search: number of knots of ik[imin, imax) that are <= x, for each lane's
-// own x. Equals the reference's branchy binary search (list.rs:69-86) on sorted knots, including
-// ties (x == knot goes up), repeated knots and NaN (-> 0). All 32 lanes must call.
+// Number of knots of ik[imin, imax) that are <= x: the reference's branchy binary search
+// (list.rs:69-86) returns imin + this count on sorted knots, including ties (x == knot goes up),
+// repeated knots and NaN (-> 0).
+//
+// The search walks the 32-ary pivot pyramid top-down. Two evaluation strategies exist:
+//  * per-thread (default): every thread descends on its own, a 6-probe branch-free bisection inside
+//    each 32-entry block (one 128-byte line per level, so the top levels live in L1 and only the
+//    sectors actually probed travel from L2);
+//  * warp-cooperative (ENTERP_COOP_SEARCH=1, kept for the ablation in profiles/): the warp serves its
+//    32 samples one after the other, lane l compares pivot l, ballot + popc picks the child. It
+//    fetches whole lines but spends a full warp instruction per level PER SAMPLE; measured on B200
+//    it is issue-bound at ~1/8 of the per-thread throughput.
 template <class R>
 __device__ __forceinline__ uint32_t coop_count_le(const CurveDev<R>& c, R x) {
   const unsigned lane = threadIdx.x & 31u;
@@ -128,6 +138,31 @@ __device__ __forceinline__ uint32_t coop_count_le(const CurveDev<R>& c, R x) {
   return mine;
 }
 
+template <class R>
+__device__ __forceinline__ uint32_t thread_count_le(const CurveDev<R>& c, R x) {
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int l = 0; l < MAX_LEVELS; ++l) {
+    if (l < c.n_lvl) {
+      const R* __restrict__ blk = c.lvl[l] + (size_t)cnt * 32u;
+      // entries <= x form a prefix of the block (sorted values, then NaN padding: NaN <= x is false)
+      uint32_t pos = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) pos += (__ldg(blk + pos + step - 1) <= x) ? step : 0;
+      pos += (__ldg(blk + pos) <= x) ? 1u : 0u;  // 31 -> 32 (only possible in the top level)
+      cnt = cnt * 32u + pos;
+    }
+  }
+  return cnt;
+}
+
+// All lanes of the warp must call (the cooperative variant shuffles).
+template <class R>
+__device__ __forceinline__ uint32_t count_le(const CurveDev<R>& c, R x) {
+  if (c.coop_search) return coop_count_le(c, x);
+  return thread_count_le(c, x);
+}
+
 // inner index -> virtual index: BorderBuffer::map_from (adaptors.rs:31-39) / BorderDeletion (-1).
 template <class R>
 __device__ __forceinline__ uint32_t map_from_inner(const CurveDev<R>& c, uint32_t inner_idx) {
@@ -145,7 +180,7 @@ __device__ __forceinline__ bool bspline_span(const CurveDev<R>& c, R x, uint32_t
     ok = equi_inner_index(c, x, inner);
     if (!ok) inner = c.imin;
   } else {
-    inner = c.imin + coop_count_le(c, x);
+    inner = c.imin + count_le(c, x);
   }
   index = map_from_inner(c, inner);
   return ok;
@@ -183,7 +218,7 @@ __device__ __forceinline__ bool linear_border(const CurveDev<R>& c, R x, uint32_
     }
     return true;
   } else {
-    const uint32_t m = coop_count_le(c, x);  // strict_upper_bound over the whole chain
+    const uint32_t m = count_le(c, x);  // strict_upper_bound over the whole chain
     const bool edge = (m == len) || (m == 0);
     imax = m == len ? len - 1 : (m == 0 ? 1u : m);
     imin = imax - 1;

@@ -193,7 +193,7 @@ __device__ __forceinline__ uint32_t rows_span(const CurveDev<R>& c, const RowsDe
     inner = (left || !valid) ? c.imin : up;
   } else {
     valid = true;
-    inner = c.imin + coop_count_le(c, x);
+    inner = c.imin + count_le(c, x);
   }
   return min(inner + rw.ri_off, rw.n_rows - 1u);  // the clamp is a no-op for every valid sample
 }
@@ -348,8 +348,15 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
   }
 }
 
+// Occupancy hint: small rows (cubic [f32;4] needs 36 row registers) fit 4 CTAs/SM under a 64-register
+// cap; bigger rows keep the default so that they do not spill.
+template <class R>
+__host__ __device__ constexpr int rows_min_blocks(int P, int DH) {
+  return row_len<R>(P, DH) * (int)(sizeof(R) / 4) <= 40 ? 4 : 1;
+}
+
 template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2>
-__global__ void __launch_bounds__(BLOCK) bspline_rows_kernel(const CurveDev<R> c, const SampleSrc<R> s,
+__global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH)) bspline_rows_kernel(const CurveDev<R> c, const SampleSrc<R> s,
                                                              R* __restrict__ out, const RowsDev<R> rw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;

@@ -13,7 +13,7 @@ import bench  # noqa: E402
 def main():
     case = sys.argv[1] if len(sys.argv) > 1 else "c5"
     log2n = int(sys.argv[2]) if len(sys.argv) > 2 else 28
-    arg3 = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    arg3 = int(sys.argv[3]) if len(sys.argv) > 3 else None
     w = bench.make_workload(case, log2n, arg3)
     for _ in range(3):
         w.step()
