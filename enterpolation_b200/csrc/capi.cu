@@ -234,7 +234,7 @@ enterp_status dispatch_eval(const Resolved& r, const Replica& rp, const SampleSr
         rw.one = R(1);
         rw.eq_rstep = (R)r.eq_rstep;
         rw.ri_off = (uint32_t)((int64_t)r.map_add - (int64_t)r.rows_lo);
-        e = launch_bspline_rows<R>(r.dh, proj, deg, equi, r.rows_mode == 1, d, s, static_cast<R*>(out), vec_ok, rw, st);
+        e = launch_bspline_rows<R>(r.dh, proj, deg, equi, r.rows_mode == 1, d, s, static_cast<R*>(out), rw, st);
       } else {
         e = launch_bspline<R>(r.dh, proj, deg, equi, d, s, static_cast<R*>(out), vec_ok, st);
       }

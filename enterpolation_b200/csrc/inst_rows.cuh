@@ -1,14 +1,12 @@
-// Span-row B-spline kernel instantiations for one (scalar type, division mode) pair.
+// Span-row B-spline kernel instantiations for one (scalar type, division mode, projection, knot base).
 #pragma once
 #include "inst_common.cuh"
 #include "rows.cuh"
 
 namespace enterp {
 
-
 template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2>
-cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok, const RowsDev<R>& rw,
-                            cudaStream_t st) {
+cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out, const RowsDev<R>& rw, cudaStream_t st) {
   auto kernel = bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2>;
   static bool configured = false;  // per instantiation; benign race (idempotent attribute)
   if (!configured) {
@@ -20,7 +18,7 @@ cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, rw.bytes) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  unsigned long long want = (s.count + ROWS_S * BLOCK - 1) / (ROWS_S * BLOCK);
+  const unsigned long long want = (s.count + ROWS_S * BLOCK - 1) / (ROWS_S * BLOCK);
   const unsigned long long cap = (unsigned long long)per_sm * (unsigned long long)sm_count();
   const int grid = (int)(want < cap ? want : cap);
   kernel<<<grid, BLOCK, rw.bytes, st>>>(c, s, out, rw);
@@ -28,39 +26,41 @@ cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
   return cudaGetLastError();
 }
 
-template <class R, int DH, bool PROJ, bool POW2>
-cudaError_t rows_pick_degree(int deg, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
-                             const RowsDev<R>& rw, cudaStream_t st) {
-#define ENTERP_ROWS(DD)                                                                          \
-  case DD:                                                                                       \
-    return equi ? rows_launch_one<R, DH, PROJ, DD, true, POW2>(c, s, out, vec_ok, rw, st)        \
-                : rows_launch_one<R, DH, PROJ, DD, false, POW2>(c, s, out, vec_ok, rw, st);
+template <class R, int DH, bool PROJ, bool EQUI, bool POW2>
+cudaError_t rows_pick_degree(int deg, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, const RowsDev<R>& rw,
+                             cudaStream_t st) {
   switch (deg) {
-    ENTERP_ROWS(1) ENTERP_ROWS(2) ENTERP_ROWS(3) ENTERP_ROWS(4) ENTERP_ROWS(5) ENTERP_ROWS(6) ENTERP_ROWS(7)
+    case 1: return rows_launch_one<R, DH, PROJ, 1, EQUI, POW2>(c, s, out, rw, st);
+    case 2: return rows_launch_one<R, DH, PROJ, 2, EQUI, POW2>(c, s, out, rw, st);
+    case 3: return rows_launch_one<R, DH, PROJ, 3, EQUI, POW2>(c, s, out, rw, st);
+    case 4: return rows_launch_one<R, DH, PROJ, 4, EQUI, POW2>(c, s, out, rw, st);
+    case 5: return rows_launch_one<R, DH, PROJ, 5, EQUI, POW2>(c, s, out, rw, st);
+    case 6: return rows_launch_one<R, DH, PROJ, 6, EQUI, POW2>(c, s, out, rw, st);
+    case 7: return rows_launch_one<R, DH, PROJ, 7, EQUI, POW2>(c, s, out, rw, st);
   }
-#undef ENTERP_ROWS
   return cudaErrorInvalidValue;
 }
 
-template <class R, bool POW2>
-cudaError_t launch_rows_impl(int dh, bool proj, int deg, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
-                             bool vec_ok, const RowsDev<R>& rw, cudaStream_t st) {
-  if (!proj) {
-    switch (dh) {
-      case 1: return rows_pick_degree<R, 1, false, POW2>(deg, equi, c, s, out, vec_ok, rw, st);
-      case 2: return rows_pick_degree<R, 2, false, POW2>(deg, equi, c, s, out, vec_ok, rw, st);
-      case 3: return rows_pick_degree<R, 3, false, POW2>(deg, equi, c, s, out, vec_ok, rw, st);
-      case 4: return rows_pick_degree<R, 4, false, POW2>(deg, equi, c, s, out, vec_ok, rw, st);
-    }
-  } else {
-    switch (dh) {
-      case 2: return rows_pick_degree<R, 2, true, POW2>(deg, equi, c, s, out, vec_ok, rw, st);
-      case 3: return rows_pick_degree<R, 3, true, POW2>(deg, equi, c, s, out, vec_ok, rw, st);
-      case 4: return rows_pick_degree<R, 4, true, POW2>(deg, equi, c, s, out, vec_ok, rw, st);
-      case 5: return rows_pick_degree<R, 5, true, POW2>(deg, equi, c, s, out, vec_ok, rw, st);
-    }
+template <class R, bool POW2, bool PROJ, bool EQUI>
+cudaError_t launch_rows_part_impl(int dh, int deg, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
+                                  const RowsDev<R>& rw, cudaStream_t st) {
+  constexpr int B = PROJ ? 1 : 0;  // weighted curves carry dim + 1 components
+  switch (dh - B) {
+    case 1: return rows_pick_degree<R, 1 + B, PROJ, EQUI, POW2>(deg, c, s, out, rw, st);
+    case 2: return rows_pick_degree<R, 2 + B, PROJ, EQUI, POW2>(deg, c, s, out, rw, st);
+    case 3: return rows_pick_degree<R, 3 + B, PROJ, EQUI, POW2>(deg, c, s, out, rw, st);
+    case 4: return rows_pick_degree<R, 4 + B, PROJ, EQUI, POW2>(deg, c, s, out, rw, st);
   }
   return cudaErrorInvalidValue;
 }
 
 }  // namespace enterp
+
+#define ENTERP_DEFINE_ROWS_PART(R, POW2, PROJ, EQUI)                                                                  \
+  namespace enterp {                                                                                                  \
+  template <>                                                                                                         \
+  cudaError_t launch_rows_part<R, POW2, PROJ, EQUI>(int dh, int deg, const CurveDev<R>& c, const SampleSrc<R>& s,     \
+                                                    R* out, const RowsDev<R>& rw, cudaStream_t st) {                  \
+    return launch_rows_part_impl<R, POW2, PROJ, EQUI>(dh, deg, c, s, out, rw, st);                                    \
+  }                                                                                                                   \
+  }

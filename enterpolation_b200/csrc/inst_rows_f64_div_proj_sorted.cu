@@ -1,0 +1,2 @@
+#include "inst_rows.cuh"
+ENTERP_DEFINE_ROWS_PART(double, false, true, false)

@@ -31,15 +31,24 @@ template <class R>
 cudaError_t launch_bspline(int dh, bool proj, int deg, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
                            bool vec_ok, cudaStream_t st);
 // Span-row fast path (rows.cuh): deg 1..7, table <= ROWS_MAX_BYTES. POW2: exact inverse multiply.
-template <class R, bool POW2>
-cudaError_t launch_bspline_rows_mode(int dh, bool proj, int deg, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s,
-                                     R* out, bool vec_ok, const RowsDev<R>& rw, cudaStream_t st);
+// One translation unit per (R, POW2, PROJ, EQUI) so that nvcc compiles them in parallel.
+template <class R, bool POW2, bool PROJ, bool EQUI>
+cudaError_t launch_rows_part(int dh, int deg, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
+                             const RowsDev<R>& rw, cudaStream_t st);
 template <class R>
 inline cudaError_t launch_bspline_rows(int dh, bool proj, int deg, bool equi, bool pow2, const CurveDev<R>& c,
-                                       const SampleSrc<R>& s, R* out, bool vec_ok, const RowsDev<R>& rw,
-                                       cudaStream_t st) {
-  return pow2 ? launch_bspline_rows_mode<R, true>(dh, proj, deg, equi, c, s, out, vec_ok, rw, st)
-              : launch_bspline_rows_mode<R, false>(dh, proj, deg, equi, c, s, out, vec_ok, rw, st);
+                                       const SampleSrc<R>& s, R* out, const RowsDev<R>& rw, cudaStream_t st) {
+  const int key = (pow2 ? 4 : 0) | (proj ? 2 : 0) | (equi ? 1 : 0);
+  switch (key) {
+    case 0: return launch_rows_part<R, false, false, false>(dh, deg, c, s, out, rw, st);
+    case 1: return launch_rows_part<R, false, false, true>(dh, deg, c, s, out, rw, st);
+    case 2: return launch_rows_part<R, false, true, false>(dh, deg, c, s, out, rw, st);
+    case 3: return launch_rows_part<R, false, true, true>(dh, deg, c, s, out, rw, st);
+    case 4: return launch_rows_part<R, true, false, false>(dh, deg, c, s, out, rw, st);
+    case 5: return launch_rows_part<R, true, false, true>(dh, deg, c, s, out, rw, st);
+    case 6: return launch_rows_part<R, true, true, false>(dh, deg, c, s, out, rw, st);
+    default: return launch_rows_part<R, true, true, true>(dh, deg, c, s, out, rw, st);
+  }
 }
 template <class R>
 cudaError_t launch_linear(int dh, bool proj, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
