@@ -45,6 +45,15 @@ static const bool g_coop_search = [] {
   return v && v[0] == '1';
 }();
 
+// Opt-in (env ENTERP_SMEM_PIVOTS=1): TMA-stage the pivot levels above the bottom one into shared memory.
+// Off by default: measured on B200 (C2, 2^20 knots, 2^28 samples) it does not pay — the upper levels
+// already live in L1, the kernel is bound by the L2 sector traffic of the bottom level and the element
+// gather, and one fat CTA per SM halves the warps in flight (20.3 vs 21.5 G samples/s).
+static const bool g_smem_pivots = [] {
+  const char* v = std::getenv("ENTERP_SMEM_PIVOTS");
+  return v && v[0] == '1';
+}();
+
 static thread_local std::string t_cuda_error;
 static enterp_status cuda_fail(cudaError_t e, const char* where) {
   t_cuda_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
@@ -87,8 +96,11 @@ struct Replica {
   void* store = nullptr;
   void* elems = nullptr;
   void* rows = nullptr;
-  void* lvl[MAX_LEVELS] = {};
+  void* pyramid = nullptr;              // all pivot levels, top first, one allocation
+  uint32_t lvl_off[MAX_LEVELS] = {};    // element offsets of the levels inside it
   int n_lvl = 0;
+  uint32_t top_bytes = 0;               // size of levels [0, n_lvl-1) when they are worth staging in smem
+  int n_top = 0;
   unsigned long long* invalid = nullptr;
   HostPipe pipe;
 };
@@ -132,14 +144,29 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   if (e == cudaSuccess) e = put(c->r.elems, &rp->elems);
   if (e == cudaSuccess && c->r.rows_mode) e = put(c->r.rows, &rp->rows);
   rp->n_lvl = (int)c->r.levels.level.size();
-  for (int l = 0; l < rp->n_lvl && e == cudaSuccess; ++l) e = put(c->r.levels.level[l], &rp->lvl[l]);
+  if (rp->n_lvl > 0 && e == cudaSuccess) {
+    std::vector<unsigned char> all;
+    const size_t rs = rsize(c->r);
+    for (int l = 0; l < rp->n_lvl; ++l) {
+      rp->lvl_off[l] = (uint32_t)(all.size() / rs);
+      all.insert(all.end(), c->r.levels.level[l].begin(), c->r.levels.level[l].end());
+    }
+    e = put(all, &rp->pyramid);
+    // Stage everything above the bottom level in shared memory when that is big enough to fall out of
+    // L1 (small pyramids stay L1-resident anyway) and small enough to fit.
+    const size_t top = (size_t)rp->lvl_off[rp->n_lvl - 1] * rs;
+    if (rp->n_lvl >= 2 && top >= 8u * 1024u && top <= SEARCH_SMEM_MAX && g_smem_pivots) {
+      rp->top_bytes = (uint32_t)top;
+      rp->n_top = rp->n_lvl - 1;
+    }
+  }
   if (e == cudaSuccess) e = cudaMalloc((void**)&rp->invalid, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(rp->invalid, 0, sizeof(unsigned long long));
   if (e != cudaSuccess) {
     cudaFree(rp->store);
     cudaFree(rp->elems);
     cudaFree(rp->rows);
-    for (int l = 0; l < MAX_LEVELS; ++l) cudaFree(rp->lvl[l]);
+    cudaFree(rp->pyramid);
     cudaFree(rp->invalid);
     delete rp;
     return cuda_fail(e, "curve upload");
@@ -162,7 +189,12 @@ CurveDev<R> make_dev(const Resolved& r, const Replica& rp) {
   d.ik = store ? store + r.ik_off : nullptr;
   d.elems = static_cast<const R*>(rp.elems);
   d.n_lvl = rp.n_lvl;
-  for (int l = 0; l < MAX_LEVELS; ++l) d.lvl[l] = static_cast<const R*>(rp.lvl[l]);
+  for (int l = 0; l < MAX_LEVELS; ++l) {
+    d.lvl_off[l] = rp.lvl_off[l];
+    d.lvl[l] = l < rp.n_lvl ? static_cast<const R*>(rp.pyramid) + rp.lvl_off[l] : nullptr;
+  }
+  d.n_top = rp.n_top;
+  d.top_bytes = rp.top_bytes;
   d.n_elem = (uint32_t)r.n_elem;
   d.inner_len = (uint32_t)r.inner_len;
   d.virt_len = (uint32_t)r.virt_len;
@@ -448,7 +480,7 @@ ENTERP_API void enterp_curve_destroy(enterp_curve* c) {
     cudaFree(rp->store);
     cudaFree(rp->elems);
     cudaFree(rp->rows);
-    for (int l = 0; l < MAX_LEVELS; ++l) cudaFree(rp->lvl[l]);
+    cudaFree(rp->pyramid);
     cudaFree(rp->invalid);
     for (int b = 0; b < 2; ++b) {
       cudaFree(rp->pipe.dev_in[b]);

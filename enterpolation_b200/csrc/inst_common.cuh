@@ -14,4 +14,35 @@ cudaError_t launch_grid_stride(K kernel, unsigned long long work_items, int item
   return cudaGetLastError();
 }
 
+// Launch for kernels that may stage `smem` bytes of pivot levels: picks the block size (one fat CTA per SM
+// when the table is big, as far as the kernel's launch bounds and registers allow) and the matching grid.
+template <class K, class... Args>
+cudaError_t launch_searching(K kernel, unsigned long long work_items, size_t smem, cudaStream_t st, Args... args) {
+  if (work_items == 0) return cudaSuccess;
+  int block = BLOCK;
+  if (smem > 0) {
+    cudaFuncAttributes fa{};
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    if (smem > 48u * 1024u) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM_MAX);
+      if (e != cudaSuccess) return e;
+    }
+    if (smem > 32u * 1024u) {  // few CTAs per SM fit: make them fat
+      int cap = fa.maxThreadsPerBlock < MAX_BLOCK ? fa.maxThreadsPerBlock : MAX_BLOCK;
+      const int by_regs = fa.numRegs > 0 ? (65536 / fa.numRegs) / 256 * 256 : cap;
+      if (by_regs < cap) cap = by_regs;
+      block = cap >= 256 ? cap : 256;
+    }
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  unsigned long long want = (work_items + block - 1) / block;
+  const unsigned long long cap_grid = (unsigned long long)per_sm * (unsigned long long)sm_count();
+  const int grid = (int)(want < cap_grid ? want : cap_grid);
+  kernel<<<grid, block, smem, st>>>(args...);
+  count_launch();
+  return cudaGetLastError();
+}
+
 }  // namespace enterp

@@ -7,7 +7,7 @@ template <class R, int DH, bool PROJ>
 static cudaError_t linear_pick(bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
                                cudaStream_t st) {
   if (equi) return launch_grid_stride(linear_kernel<R, DH, PROJ, true>, s.count, BLOCK, st, c, s, out, vec_ok);
-  return launch_grid_stride(linear_kernel<R, DH, PROJ, false>, s.count, BLOCK, st, c, s, out, vec_ok);
+  return launch_searching(linear_kernel<R, DH, PROJ, false>, s.count, c.top_bytes, st, c, s, out, vec_ok);
 }
 
 template <class R>

@@ -15,14 +15,19 @@ constexpr int MAX_LEVELS = 7;     // 32^7 > 2^31 searched knots
 constexpr int MAX_DYN_DEGREE = 63;  // runtime-degree de Boor keeps its workspace in local memory
 constexpr int MAX_DYN_BEZIER = 256;
 constexpr int BLOCK = 256;
+constexpr int MAX_BLOCK = 1024;        // kernels that stage big pivot tables run one fat CTA per SM
+constexpr unsigned SEARCH_SMEM_MAX = 160u * 1024u;  // shared-memory budget for staged pivot levels
 
 template <class R>
 struct CurveDev {
   const R* vk;     // virtual knot vector (BorderBuffer / BorderDeletion already applied)
   const R* ik;     // innermost knot chain (what the search runs on)
   const R* elems;  // [n_elem][DH], homogeneous-lifted when weighted
-  const R* lvl[MAX_LEVELS];  // 32-ary pivot pyramid, top level first, NaN padded
+  const R* lvl[MAX_LEVELS];  // 32-ary pivot pyramid, top level first, NaN padded (one contiguous buffer)
+  uint32_t lvl_off[MAX_LEVELS];  // offset of each level inside that buffer, in elements
   int n_lvl;
+  int n_top;           // levels [0, n_top) are staged into shared memory by the kernel (0: none)
+  uint32_t top_bytes;  // their total size (multiple of 128)
   uint32_t n_elem, inner_len, virt_len, degree;
   uint32_t imin, imax, map0, mapL;
   int32_t map_add;
@@ -106,6 +111,35 @@ __device__ __forceinline__ bool equi_inner_index(const CurveDev<R>& c, R x, uint
   return true;
 }
 
+// ---- TMA bulk staging: one elected thread issues cp.async.bulk global->shared, everyone waits on the
+// mbarrier (SASS: UBLKCP + SYNCS). `bytes` must be a multiple of 16 and < 2^20.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_stage(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* mbar) {
+  if (threadIdx.x == 0) {
+    const uint32_t bar = smem_u32(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  __syncthreads();  // barrier initialised and copy issued before anyone waits
+  const uint32_t bar = smem_u32(mbar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar)
+      : "memory");
+}
+
 // Number of knots of ik[imin, imax) that are <= x: the reference's branchy binary search
 // (list.rs:69-86) returns imin + this count on sorted knots, including ties (x == knot goes up),
 // repeated knots and NaN (-> 0).
@@ -138,19 +172,32 @@ __device__ __forceinline__ uint32_t coop_count_le(const CurveDev<R>& c, R x) {
   return mine;
 }
 
+// 6-probe branch-free bisection inside one 32-entry block: entries <= x form a prefix (sorted values,
+// then NaN padding: NaN <= x is false).
+template <class R, bool SMEM>
+__device__ __forceinline__ uint32_t block_count_le(const R* __restrict__ blk, R x) {
+  uint32_t pos = 0;
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const R v = SMEM ? blk[pos + step - 1] : __ldg(blk + pos + step - 1);
+    pos += (v <= x) ? step : 0;
+  }
+  const R last = SMEM ? blk[pos] : __ldg(blk + pos);
+  pos += (last <= x) ? 1u : 0u;  // 31 -> 32 (only possible in the top level)
+  return pos;
+}
+
+// `top`: shared-memory copy of levels [0, n_top) (nullptr when nothing is staged).
 template <class R>
-__device__ __forceinline__ uint32_t thread_count_le(const CurveDev<R>& c, R x) {
+__device__ __forceinline__ uint32_t thread_count_le(const CurveDev<R>& c, R x, const R* __restrict__ top) {
   uint32_t cnt = 0;
 #pragma unroll
   for (int l = 0; l < MAX_LEVELS; ++l) {
     if (l < c.n_lvl) {
-      const R* __restrict__ blk = c.lvl[l] + (size_t)cnt * 32u;
-      // entries <= x form a prefix of the block (sorted values, then NaN padding: NaN <= x is false)
-      uint32_t pos = 0;
-#pragma unroll
-      for (int step = 16; step >= 1; step >>= 1) pos += (__ldg(blk + pos + step - 1) <= x) ? step : 0;
-      pos += (__ldg(blk + pos) <= x) ? 1u : 0u;  // 31 -> 32 (only possible in the top level)
-      cnt = cnt * 32u + pos;
+      if (top != nullptr && l < c.n_top)
+        cnt = cnt * 32u + block_count_le<R, true>(top + c.lvl_off[l] + (size_t)cnt * 32u, x);
+      else
+        cnt = cnt * 32u + block_count_le<R, false>(c.lvl[l] + (size_t)cnt * 32u, x);
     }
   }
   return cnt;
@@ -158,9 +205,19 @@ __device__ __forceinline__ uint32_t thread_count_le(const CurveDev<R>& c, R x) {
 
 // All lanes of the warp must call (the cooperative variant shuffles).
 template <class R>
-__device__ __forceinline__ uint32_t count_le(const CurveDev<R>& c, R x) {
+__device__ __forceinline__ uint32_t count_le(const CurveDev<R>& c, R x, const R* __restrict__ top = nullptr) {
   if (c.coop_search) return coop_count_le(c, x);
-  return thread_count_le(c, x);
+  return thread_count_le(c, x, top);
+}
+
+// Stages the top pyramid levels into dynamic shared memory when the host asked for it; returns the
+// shared-memory base or nullptr. Must be called by every thread of the block.
+template <class R>
+__device__ __forceinline__ const R* stage_top_levels(const CurveDev<R>& c, unsigned char* smem_raw,
+                                                     unsigned long long* mbar) {
+  if (c.top_bytes == 0) return nullptr;
+  tma_stage(smem_raw, c.lvl[0], c.top_bytes, mbar);
+  return reinterpret_cast<const R*>(smem_raw);
 }
 
 // inner index -> virtual index: BorderBuffer::map_from (adaptors.rs:31-39) / BorderDeletion (-1).
@@ -173,14 +230,14 @@ __device__ __forceinline__ uint32_t map_from_inner(const CurveDev<R>& c, uint32_
 
 // BSpline span: knots.strict_upper_bound_clamped(x, degree, len - degree) (bspline/mod.rs:148-154).
 template <class R, bool EQUI>
-__device__ __forceinline__ bool bspline_span(const CurveDev<R>& c, R x, uint32_t& index) {
+__device__ __forceinline__ bool bspline_span(const CurveDev<R>& c, R x, uint32_t& index, const R* __restrict__ top = nullptr) {
   uint32_t inner;
   bool ok = true;
   if (EQUI) {
     ok = equi_inner_index(c, x, inner);
     if (!ok) inner = c.imin;
   } else {
-    inner = c.imin + count_le(c, x);
+    inner = c.imin + count_le(c, x, top);
   }
   index = map_from_inner(c, inner);
   return ok;
@@ -188,7 +245,8 @@ __device__ __forceinline__ bool bspline_span(const CurveDev<R>& c, R x, uint32_t
 
 // Linear span: knots.upper_border(x) -> (min, max, factor) (list.rs:169-248 / 532-551).
 template <class R, bool EQUI>
-__device__ __forceinline__ bool linear_border(const CurveDev<R>& c, R x, uint32_t& imin, uint32_t& imax, R& factor) {
+__device__ __forceinline__ bool linear_border(const CurveDev<R>& c, R x, uint32_t& imin, uint32_t& imax, R& factor,
+                                              const R* __restrict__ top = nullptr) {
   const uint32_t len = c.inner_len;
   if (EQUI) {
     const R scaled = xdiv(xsub(x, c.eq_offset), c.eq_step);
@@ -218,7 +276,7 @@ __device__ __forceinline__ bool linear_border(const CurveDev<R>& c, R x, uint32_
     }
     return true;
   } else {
-    const uint32_t m = count_le(c, x);  // strict_upper_bound over the whole chain
+    const uint32_t m = count_le(c, x, top);  // strict_upper_bound over the whole chain
     const bool edge = (m == len) || (m == 0);
     imax = m == len ? len - 1 : (m == 0 ? 1u : m);
     imin = imax - 1;
@@ -273,22 +331,33 @@ __device__ __forceinline__ void finish_and_store(R* __restrict__ out, unsigned l
   store_elem<R, D>(out, i, v, vec_ok);
 }
 
+// Largest block the generic B-spline kernel may be launched with: 1024 threads (one fat CTA per SM, used
+// when big pivot tables are staged in shared memory) only where the register working set fits the
+// 64-register cap that implies; otherwise 256.
+template <class R>
+__host__ __device__ constexpr int bspline_block_cap(int DEG, int DH) {
+  return (DEG == 0 || (int)(sizeof(R) / 4) * (2 * DEG + (DEG + 1) * DH + 8) <= 48) ? MAX_BLOCK : BLOCK;
+}
+
 // =================================================================================================
 // BSpline: span -> gather degree+1 elements and 2*degree knots -> de Boor (bspline/mod.rs:145-169)
 // DEG == 0: runtime degree (DynSpace semantics; workspace in local memory).
 // =================================================================================================
 template <class R, int DH, bool PROJ, int DEG, bool EQUI>
-__global__ void __launch_bounds__(BLOCK) bspline_kernel(const CurveDev<R> c, const SampleSrc<R> s, R* __restrict__ out,
+__global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(const CurveDev<R> c, const SampleSrc<R> s, R* __restrict__ out,
                                                         const bool vec_ok) {
   constexpr int P_CAP = DEG > 0 ? DEG : MAX_DYN_DEGREE;
   const int p = DEG > 0 ? DEG : (int)c.degree;
-  for (unsigned long long base = (unsigned long long)blockIdx.x * BLOCK; base < s.count;
-       base += (unsigned long long)gridDim.x * BLOCK) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const R* __restrict__ top = EQUI ? nullptr : stage_top_levels(c, smem_raw, &mbar);
+  for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < s.count;
+       base += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long i = base + threadIdx.x;
     const bool active = i < s.count;
     R x = active ? sample_param(s, i) : c.eq_first;
     uint32_t index;
-    bool valid = bspline_span<R, EQUI>(c, x, index);
+    bool valid = bspline_span<R, EQUI>(c, x, index, top);
     if (!active) continue;
     const uint32_t first = index - (uint32_t)p;
     R kn[2 * P_CAP];
@@ -333,16 +402,19 @@ __global__ void __launch_bounds__(BLOCK) bspline_kernel(const CurveDev<R> c, con
 // Linear: upper_border -> two element fetches -> merge (linear/mod.rs:122-128), Identity easing.
 // =================================================================================================
 template <class R, int DH, bool PROJ, bool EQUI>
-__global__ void __launch_bounds__(BLOCK) linear_kernel(const CurveDev<R> c, const SampleSrc<R> s, R* __restrict__ out,
+__global__ void __launch_bounds__(MAX_BLOCK) linear_kernel(const CurveDev<R> c, const SampleSrc<R> s, R* __restrict__ out,
                                                        const bool vec_ok) {
-  for (unsigned long long base = (unsigned long long)blockIdx.x * BLOCK; base < s.count;
-       base += (unsigned long long)gridDim.x * BLOCK) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const R* __restrict__ top = EQUI ? nullptr : stage_top_levels(c, smem_raw, &mbar);
+  for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < s.count;
+       base += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long i = base + threadIdx.x;
     const bool active = i < s.count;
     R x = active ? sample_param(s, i) : R(0);
     uint32_t imin, imax;
     R f;
-    const bool valid = linear_border<R, EQUI>(c, x, imin, imax, f);
+    const bool valid = linear_border<R, EQUI>(c, x, imin, imax, f, top);
     if (!active) continue;
     const R omf = xsub(R(1), f);
     R w[DH];

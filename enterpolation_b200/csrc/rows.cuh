@@ -129,34 +129,6 @@ __device__ __forceinline__ bool in_guard(R a) {
   return (m >= PK<R>::guard_lo()) && (m <= PK<R>::guard_hi());
 }
 
-// ---- TMA bulk staging ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void stage_rows(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* mbar) {
-  if (threadIdx.x == 0) {
-    const uint32_t bar = smem_u32(mbar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(bar)
-                 : "memory");
-  }
-  __syncthreads();  // barrier initialised and copy issued before anyone waits
-  const uint32_t bar = smem_u32(mbar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar)
-      : "memory");
-}
-
 // =================================================================================================
 // Branch-light equidistant span (Equidistant::strict_upper_bound_clamped, list.rs:476-488) returning
 // the ROW index directly: ri = map_from(inner) - lo = inner + ri_off when neither map_from special
@@ -362,7 +334,7 @@ __global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH)) bspline_ro
                                                              R* __restrict__ out, const RowsDev<R> rw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
-  stage_rows(smem_raw, rw.table, rw.bytes, &mbar);
+  tma_stage(smem_raw, rw.table, rw.bytes, &mbar);
   const R* __restrict__ tab = reinterpret_cast<const R*>(smem_raw);
   if (s.t) {
     rows_body<R, DH, PROJ, DEG, EQUI, POW2, false, true>(c, s, out, rw, tab);
