@@ -8,7 +8,7 @@
 The package is a thin host mirror of the reference's `Signal`/`Curve` surface; all arithmetic runs
 in hand-written sm_100a kernels inside libenterp_b200.so (see include/enterp.h). No CPU fallback.
 """
-from . import _abi
+from . import _abi, easing
 from .builders import Bezier, BezierBuilder, BSpline, BSplineBuilder, Linear, LinearBuilder
 from .curve import Curve, Take, bezier_many_take, stepper_device
 from .errors import (BezierError, BSplineError, DeviceError, Empty, EnterpolationError,

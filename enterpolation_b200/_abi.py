@@ -34,6 +34,7 @@ EQ_BY_DEGREE, EQ_BY_QUANTITY = 0, 1
 EQ_DOMAIN, EQ_NORMALIZED, EQ_DISTANCE = 0, 1, 2
 SPACE_CONSTANT, SPACE_DYNAMIC, SPACE_WORKSPACE = 0, 1, 2
 INPUT_NORMALIZED, INPUT_DOMAIN = 0, 1
+EASE_IDENTITY, EASE_FLIP, EASE_SMOOTHSTART, EASE_SMOOTHEND, EASE_SMOOTHSTEP, EASE_SMOOTHERSTEP, EASE_PLATEAU = range(7)
 
 NP_DTYPE = {F32: np.float32, F64: np.float64}
 
@@ -48,6 +49,7 @@ class CurveDesc(C.Structure):
         ("eq_count", C.c_uint64), ("eq_a", C.c_double), ("eq_b", C.c_double),
         ("space", C.c_int32), ("input_form", C.c_int32),
         ("workspace_n", C.c_uint64), ("in_a", C.c_double), ("in_b", C.c_double),
+        ("easing", C.c_int32), ("easing_n", C.c_int32), ("easing_param", C.c_double),
     ]
 
 
@@ -70,7 +72,7 @@ class CurveInfo(C.Structure):
 # every symbol include/enterp.h declares (tests check the built library exports all of them)
 EXPORTS = [
     "enterp_curve_validate", "enterp_curve_create", "enterp_curve_destroy", "enterp_curve_get_info", "enterp_curve_domain",
-    "enterp_curve_upload", "enterp_eval_batch", "enterp_eval_take", "enterp_span_batch",
+    "enterp_curve_clamp", "enterp_curve_slice", "enterp_curve_upload", "enterp_eval_batch", "enterp_eval_take", "enterp_span_batch",
     "enterp_span_take", "enterp_stepper", "enterp_bezier_many_take", "enterp_sample_host",
     "enterp_take_host", "enterp_host_alloc", "enterp_host_free", "enterp_invalid_count",
     "enterp_status_str", "enterp_last_cuda_error", "enterp_device_count", "enterp_launch_count",
@@ -107,6 +109,10 @@ def load_library() -> C.CDLL:
     lib.enterp_curve_get_info.restype = i32
     lib.enterp_curve_domain.argtypes = [vp, C.POINTER(C.c_double * 2)]
     lib.enterp_curve_domain.restype = i32
+    lib.enterp_curve_clamp.argtypes = [vp, C.POINTER(vp)]
+    lib.enterp_curve_clamp.restype = i32
+    lib.enterp_curve_slice.argtypes = [vp, i32, C.c_double, i32, C.c_double, C.POINTER(vp)]
+    lib.enterp_curve_slice.restype = i32
     lib.enterp_curve_upload.argtypes = [vp, i32]
     lib.enterp_curve_upload.restype = i32
     lib.enterp_eval_batch.argtypes = [vp, i32, vp, u64, vp, vp]
@@ -154,7 +160,7 @@ class DescArrays:
 
 
 def make_desc(kind, scalar, elements, weights=None, *, mode=OPEN, knots=None, equidistant=None,
-              space=(SPACE_DYNAMIC, 0), bezier_domain=None) -> DescArrays:
+              space=(SPACE_DYNAMIC, 0), bezier_domain=None, easing=(EASE_IDENTITY, 0, 0.0)) -> DescArrays:
     """Flatten one finished builder chain into the C descriptor.
 
     elements: array-like [n] or [n][dim]; weights: [n] or None; knots: [k] or None;
@@ -195,6 +201,7 @@ def make_desc(kind, scalar, elements, weights=None, *, mode=OPEN, knots=None, eq
     else:
         d.knot_base = KNOTS_SORTED if kind != BEZIER else 0
     d.space, d.workspace_n = space
+    d.easing, d.easing_n, d.easing_param = int(easing[0]), int(easing[1]), float(dt(easing[2]))
     if bezier_domain is not None:
         d.input_form = INPUT_DOMAIN
         d.in_a, d.in_b = float(dt(bezier_domain[0])), float(dt(bezier_domain[1]))

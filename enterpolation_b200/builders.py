@@ -63,6 +63,7 @@ class _Chain:
         self._eq = None           # [eq_by, eq_count, eq_form, a, b]
         self._space = (_abi.SPACE_DYNAMIC, 0)
         self._bezier_domain = None
+        self._easing = (_abi.EASE_IDENTITY, 0, 0.0)
         self._device = 0
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -82,7 +83,7 @@ class _Chain:
         return _abi.make_desc(self._kind, self._resolved_scalar(),
                               [] if self._elements is None else self._elements, self._weights,
                               mode=self._mode, knots=self._knots, equidistant=eq, space=self._space,
-                              bezier_domain=self._bezier_domain)
+                              bezier_domain=self._bezier_domain, easing=self._easing)
 
     def _validate(self, stage: int):
         """Ask the C library whether the chain so far is valid (Director semantics)."""
@@ -169,9 +170,15 @@ class LinearBuilder(_Chain, _ElementsMixin, _EquidistantMixin):
         return self
 
     def easing(self, easing):
-        """Only `Identity` (the default) crosses to the device."""
-        if easing is not None and easing != "identity":
-            raise NotImplementedError("only the Identity easing is offloaded")
+        """`.easing(F)` (linear/builder.rs:496-503): one of the built-ins in enterpolation_b200.easing
+        (Identity, flip, smoothstart(n), smoothend(n), smoothstep, smootherstep, Plateau(strength))."""
+        from .easing import Easing
+        if easing is None:
+            self._easing = (_abi.EASE_IDENTITY, 0, 0.0)
+        elif isinstance(easing, Easing):
+            self._easing = easing.triple()
+        else:
+            raise NotImplementedError("only the built-in easings cross to the device; closures (FuncEase) cannot")
         return self
 
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -79,7 +80,9 @@ struct DeviceGuard {
   }
 };
 
-// Scratch of the host-buffer pipelines (double buffered), cached per replica.
+// Scratch of the host-buffer pipelines (double buffered): one per DEVICE, shared by every curve, so
+// that a freshly built curve does not pay for device/pinned allocations (a build() + collect() step
+// is then bound by PCIe alone). Calls on one device serialise on the pipe's mutex.
 struct HostPipe {
   void* dev_in[2] = {nullptr, nullptr};
   void* dev_out[2] = {nullptr, nullptr};
@@ -102,17 +105,49 @@ struct Replica {
   uint32_t top_bytes = 0;               // size of levels [0, n_lvl-1) when they are worth staging in smem
   int n_top = 0;
   unsigned long long* invalid = nullptr;
-  HostPipe pipe;
 };
+
+static HostPipe* device_pipe(int device) {
+  static std::mutex mu;
+  static std::vector<HostPipe*> pipes;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)pipes.size() <= device) pipes.resize(device + 1, nullptr);
+  if (!pipes[device]) pipes[device] = new HostPipe();  // lives until process exit
+  return pipes[device];
+}
 
 }  // namespace enterp
 
 using namespace enterp;
 
-struct enterp_curve {
+// Tables + device replicas, shared by a curve and the handles derived from it (clamp / slice).
+struct CurveCore {
   Resolved r;
   std::mutex mu;
   std::vector<Replica*> replicas;  // index = device ordinal
+  ~CurveCore() {
+    for (Replica* rp : replicas) {
+      if (!rp) continue;
+      DeviceGuard g(rp->device);
+      cudaFree(rp->store);
+      cudaFree(rp->elems);
+      cudaFree(rp->rows);
+      cudaFree(rp->pyramid);
+      cudaFree(rp->invalid);
+      delete rp;
+    }
+  }
+};
+
+// One input adaptor (base/adaptors.rs): kind 0 = Clamp(a = lo, b = hi), 1 = affine t * a + b.
+struct PreOp {
+  int kind;
+  double a, b;  // exact R values widened to double
+};
+
+struct enterp_curve {
+  std::shared_ptr<CurveCore> core;
+  std::vector<PreOp> pre;  // outermost adaptor first; a Bezier .domain(a,b) transform is the innermost
 };
 
 namespace {
@@ -124,9 +159,9 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   int n = 0;
   CK(cudaGetDeviceCount(&n), "cudaGetDeviceCount");
   if (device >= n) return ENTERP_NO_DEVICE;
-  if ((int)c->replicas.size() <= device) c->replicas.resize(device + 1, nullptr);
-  if (c->replicas[device]) {
-    *out = c->replicas[device];
+  if ((int)c->core->replicas.size() <= device) c->core->replicas.resize(device + 1, nullptr);
+  if (c->core->replicas[device]) {
+    *out = c->core->replicas[device];
     return ENTERP_OK;
   }
   DeviceGuard g(device);
@@ -140,16 +175,16 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dev, host.data(), host.size(), cudaMemcpyHostToDevice);
   };
-  cudaError_t e = put(c->r.store, &rp->store);
-  if (e == cudaSuccess) e = put(c->r.elems, &rp->elems);
-  if (e == cudaSuccess && c->r.rows_mode) e = put(c->r.rows, &rp->rows);
-  rp->n_lvl = (int)c->r.levels.level.size();
+  cudaError_t e = put(c->core->r.store, &rp->store);
+  if (e == cudaSuccess) e = put(c->core->r.elems, &rp->elems);
+  if (e == cudaSuccess && c->core->r.rows_mode) e = put(c->core->r.rows, &rp->rows);
+  rp->n_lvl = (int)c->core->r.levels.level.size();
   if (rp->n_lvl > 0 && e == cudaSuccess) {
     std::vector<unsigned char> all;
-    const size_t rs = rsize(c->r);
+    const size_t rs = rsize(c->core->r);
     for (int l = 0; l < rp->n_lvl; ++l) {
       rp->lvl_off[l] = (uint32_t)(all.size() / rs);
-      all.insert(all.end(), c->r.levels.level[l].begin(), c->r.levels.level[l].end());
+      all.insert(all.end(), c->core->r.levels.level[l].begin(), c->core->r.levels.level[l].end());
     }
     e = put(all, &rp->pyramid);
     // Stage everything above the bottom level in shared memory when that is big enough to fall out of
@@ -171,18 +206,19 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
     delete rp;
     return cuda_fail(e, "curve upload");
   }
-  c->replicas[device] = rp;
+  c->core->replicas[device] = rp;
   *out = rp;
   return ENTERP_OK;
 }
 
 enterp_status get_replica(enterp_curve* c, int device, Replica** out) {
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::lock_guard<std::mutex> lk(c->core->mu);
   return upload_locked(c, device, out);
 }
 
 template <class R>
-CurveDev<R> make_dev(const Resolved& r, const Replica& rp) {
+CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
+  const Resolved& r = cv.core->r;
   CurveDev<R> d{};
   const R* store = static_cast<const R*>(rp.store);
   d.vk = store ? store + r.vk_off : nullptr;
@@ -208,9 +244,16 @@ CurveDev<R> make_dev(const Resolved& r, const Replica& rp) {
   d.eq_offset = (R)r.eq_offset;
   d.eq_first = (R)r.eq_first;
   d.eq_lenm2 = r.inner_len >= 2 ? (R)(r.inner_len - 2) : R(0);  // from_usize(len - 2), list.rs:546
-  d.in_add = (R)r.in_add;
-  d.in_mul = (R)r.in_mul;
-  d.has_transform = r.has_transform;
+  d.n_pre = (int)cv.pre.size();
+  for (int i = 0; i < d.n_pre && i < MAX_PRE; ++i) {
+    d.pre_kind[i] = cv.pre[i].kind;
+    d.pre_a[i] = (R)cv.pre[i].a;
+    d.pre_b[i] = (R)cv.pre[i].b;
+  }
+  d.easing = r.easing;
+  d.easing_n = r.easing_n;
+  d.ease_min = (R)r.ease_min;
+  d.ease_max = (R)r.ease_max;
   d.coop_search = g_coop_search ? 1 : 0;
   d.invalid = rp.invalid;
   return d;
@@ -242,8 +285,9 @@ SampleSrc<R> batch_src(const void* t, uint64_t n) {
 }
 
 template <class R>
-enterp_status dispatch_eval(const Resolved& r, const Replica& rp, const SampleSrc<R>& s, void* out, cudaStream_t st) {
-  const CurveDev<R> d = make_dev<R>(r, rp);
+enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const SampleSrc<R>& s, void* out, cudaStream_t st) {
+  const Resolved& r = cv.core->r;
+  const CurveDev<R> d = make_dev<R>(cv, rp);
   const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 16u) == 0;
   const bool proj = r.weighted != 0;
   const bool equi = r.knot_base == ENTERP_KNOTS_EQUIDISTANT;
@@ -257,7 +301,7 @@ enterp_status dispatch_eval(const Resolved& r, const Replica& rp, const SampleSr
       // equidistant knots a span division the kernel can do exactly without the IEEE divide.
       const bool map_simple = (r.imin > 0 && r.imax < r.inner_len) || r.adaptor == AD_NONE;
       const bool eq_ok = !equi || (r.rows_mode == 1 ? r.eq_mode == 1 : r.eq_mode >= 1);
-      if (r.rows_mode && rp.rows && deg > 0 && vec_ok && map_simple && eq_ok && !g_disable_rows) {
+      if (r.rows_mode && rp.rows && deg > 0 && vec_ok && map_simple && eq_ok && cv.pre.empty() && !g_disable_rows) {
         RowsDev<R> rw{};
         rw.table = static_cast<const R*>(rp.rows);
         rw.n_rows = r.rows_n;
@@ -298,12 +342,12 @@ enterp_status eval_common(enterp_curve* c, int device, bool take, const void* t,
   DeviceGuard g(device);
   if (!g.ok) return ENTERP_NO_DEVICE;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  if (c->r.scalar == ENTERP_F32) {
-    auto s = take ? take_src<float>(c->r, n_total, first, count) : batch_src<float>(t, count);
-    return dispatch_eval<float>(c->r, *rp, s, out, cs);
+  if (c->core->r.scalar == ENTERP_F32) {
+    auto s = take ? take_src<float>(c->core->r, n_total, first, count) : batch_src<float>(t, count);
+    return dispatch_eval<float>(*c, *rp, s, out, cs);
   }
-  auto s = take ? take_src<double>(c->r, n_total, first, count) : batch_src<double>(t, count);
-  return dispatch_eval<double>(c->r, *rp, s, out, cs);
+  auto s = take ? take_src<double>(c->core->r, n_total, first, count) : batch_src<double>(t, count);
+  return dispatch_eval<double>(*c, *rp, s, out, cs);
 }
 
 enterp_status span_common(enterp_curve* c, int device, bool take, const void* t, uint64_t n_total, uint64_t first,
@@ -318,14 +362,14 @@ enterp_status span_common(enterp_curve* c, int device, bool take, const void* t,
   DeviceGuard g(device);
   if (!g.ok) return ENTERP_NO_DEVICE;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  const bool equi = c->r.knot_base == ENTERP_KNOTS_EQUIDISTANT;
+  const bool equi = c->core->r.knot_base == ENTERP_KNOTS_EQUIDISTANT;
   cudaError_t e;
-  if (c->r.scalar == ENTERP_F32) {
-    auto s = take ? take_src<float>(c->r, n_total, first, count) : batch_src<float>(t, count);
-    e = launch_span<float>(c->r.kind, equi, make_dev<float>(c->r, *rp), s, idx, static_cast<float*>(factor), cs);
+  if (c->core->r.scalar == ENTERP_F32) {
+    auto s = take ? take_src<float>(c->core->r, n_total, first, count) : batch_src<float>(t, count);
+    e = launch_span<float>(c->core->r.kind, equi, make_dev<float>(*c, *rp), s, idx, static_cast<float*>(factor), cs);
   } else {
-    auto s = take ? take_src<double>(c->r, n_total, first, count) : batch_src<double>(t, count);
-    e = launch_span<double>(c->r.kind, equi, make_dev<double>(c->r, *rp), s, idx, static_cast<double*>(factor), cs);
+    auto s = take ? take_src<double>(c->core->r, n_total, first, count) : batch_src<double>(t, count);
+    e = launch_span<double>(c->core->r.kind, equi, make_dev<double>(*c, *rp), s, idx, static_cast<double*>(factor), cs);
   }
   if (e != cudaSuccess) return cuda_fail(e, "span kernel launch");
   return ENTERP_OK;
@@ -366,10 +410,10 @@ enterp_status host_common(enterp_curve* c, int device, bool take, const void* t_
   if (st) return st;
   DeviceGuard g(device);
   if (!g.ok) return ENTERP_NO_DEVICE;
-  HostPipe& hp = rp->pipe;
+  HostPipe& hp = *device_pipe(device);
   std::lock_guard<std::mutex> lk(hp.mu);
-  const size_t rs = rsize(c->r);
-  const size_t out_stride = rs * c->r.dim;
+  const size_t rs = rsize(c->core->r);
+  const size_t out_stride = rs * c->core->r.dim;
   const uint64_t chunk = count < HOST_CHUNK ? count : HOST_CHUNK;
   const bool pin_in = take || is_pinned(t_host);
   const bool pin_out = is_pinned(out_host);
@@ -430,12 +474,12 @@ enterp_status host_common(enterp_curve* c, int device, bool take, const void* t_
       t_dev = hp.dev_in[b];
     }
     enterp_status es;
-    if (c->r.scalar == ENTERP_F32) {
-      auto s = take ? take_src<float>(c->r, n_total, first + off, n) : batch_src<float>(t_dev, n);
-      es = dispatch_eval<float>(c->r, *rp, s, hp.dev_out[b], hp.stream[b]);
+    if (c->core->r.scalar == ENTERP_F32) {
+      auto s = take ? take_src<float>(c->core->r, n_total, first + off, n) : batch_src<float>(t_dev, n);
+      es = dispatch_eval<float>(*c, *rp, s, hp.dev_out[b], hp.stream[b]);
     } else {
-      auto s = take ? take_src<double>(c->r, n_total, first + off, n) : batch_src<double>(t_dev, n);
-      es = dispatch_eval<double>(c->r, *rp, s, hp.dev_out[b], hp.stream[b]);
+      auto s = take ? take_src<double>(c->core->r, n_total, first + off, n) : batch_src<double>(t_dev, n);
+      es = dispatch_eval<double>(*c, *rp, s, hp.dev_out[b], hp.stream[b]);
     }
     if (es) return es;
     void* dst = pin_out ? static_cast<void*>(static_cast<char*>(out_host) + off * out_stride) : hp.stage_out[b];
@@ -463,41 +507,61 @@ ENTERP_API enterp_status enterp_curve_create(const enterp_curve_desc* desc, ente
   if (out) *out = nullptr;
   if (!desc || !out) return ENTERP_INVALID_ARGUMENT;
   enterp_curve* c = new enterp_curve();
-  enterp_status st = resolve(*desc, c->r, err);
+  c->core = std::make_shared<CurveCore>();
+  enterp_status st = resolve(*desc, c->core->r, err);
   if (st) {
     delete c;
     return st;
   }
+  if (c->core->r.has_transform) c->pre.push_back(PreOp{1, c->core->r.in_mul, c->core->r.in_add});
   *out = c;
   return ENTERP_OK;
 }
 
-ENTERP_API void enterp_curve_destroy(enterp_curve* c) {
-  if (!c) return;
-  for (Replica* rp : c->replicas) {
-    if (!rp) continue;
-    DeviceGuard g(rp->device);
-    cudaFree(rp->store);
-    cudaFree(rp->elems);
-    cudaFree(rp->rows);
-    cudaFree(rp->pyramid);
-    cudaFree(rp->invalid);
-    for (int b = 0; b < 2; ++b) {
-      cudaFree(rp->pipe.dev_in[b]);
-      cudaFree(rp->pipe.dev_out[b]);
-      if (rp->pipe.stage_in[b]) cudaFreeHost(rp->pipe.stage_in[b]);
-      if (rp->pipe.stage_out[b]) cudaFreeHost(rp->pipe.stage_out[b]);
-      if (rp->pipe.stream[b]) cudaStreamDestroy(rp->pipe.stream[b]);
-      if (rp->pipe.done[b]) cudaEventDestroy(rp->pipe.done[b]);
-    }
-    delete rp;
+ENTERP_API void enterp_curve_destroy(enterp_curve* c) { delete c; }  // the core goes with its last handle
+
+// Curve::clamp() -> Clamp (base/adaptors.rs:14-44): clamp(input, domain) before the wrapped eval.
+ENTERP_API enterp_status enterp_curve_clamp(const enterp_curve* base, enterp_curve** out) {
+  if (out) *out = nullptr;
+  if (!base || !out) return ENTERP_INVALID_ARGUMENT;
+  if (base->pre.size() >= (size_t)MAX_PRE) return ENTERP_UNSUPPORTED;
+  enterp_curve* c = new enterp_curve(*base);
+  c->pre.insert(c->pre.begin(), PreOp{0, base->core->r.domain[0], base->core->r.domain[1]});
+  *out = c;
+  return ENTERP_OK;
+}
+
+// Curve::slice(bounds) -> Slice::new (base/adaptors.rs:61-81): TransformInput::new(signal,
+// bound_start - signal_start, (bound_end - bound_start) / (signal_end - signal_start)), all in R arithmetic.
+ENTERP_API enterp_status enterp_curve_slice(const enterp_curve* base, int has_start, double start, int has_end,
+                                            double end, enterp_curve** out) {
+  if (out) *out = nullptr;
+  if (!base || !out) return ENTERP_INVALID_ARGUMENT;
+  if (base->pre.size() >= (size_t)MAX_PRE) return ENTERP_UNSUPPORTED;
+  const Resolved& r = base->core->r;
+  double mul, add;
+  if (r.scalar == ENTERP_F32) {
+    const float s0 = (float)r.domain[0], s1 = (float)r.domain[1];
+    const float b0 = has_start ? (float)start : s0, b1 = has_end ? (float)end : s1;
+    const float num = b1 - b0, den = s1 - s0;
+    mul = num / den;
+    add = b0 - s0;
+  } else {
+    const double s0 = r.domain[0], s1 = r.domain[1];
+    const double b0 = has_start ? start : s0, b1 = has_end ? end : s1;
+    const double num = b1 - b0, den = s1 - s0;
+    mul = num / den;
+    add = b0 - s0;
   }
-  delete c;
+  enterp_curve* c = new enterp_curve(*base);
+  c->pre.insert(c->pre.begin(), PreOp{1, mul, add});
+  *out = c;
+  return ENTERP_OK;
 }
 
 ENTERP_API enterp_status enterp_curve_get_info(const enterp_curve* c, enterp_curve_info* info) {
   if (!c || !info) return ENTERP_INVALID_ARGUMENT;
-  const Resolved& r = c->r;
+  const Resolved& r = c->core->r;
   info->kind = r.kind;
   info->scalar = r.scalar;
   info->dim = r.dim;
@@ -515,8 +579,8 @@ ENTERP_API enterp_status enterp_curve_get_info(const enterp_curve* c, enterp_cur
 
 ENTERP_API enterp_status enterp_curve_domain(const enterp_curve* c, double out[2]) {
   if (!c || !out) return ENTERP_INVALID_ARGUMENT;
-  out[0] = c->r.domain[0];
-  out[1] = c->r.domain[1];
+  out[0] = c->core->r.domain[0];
+  out[1] = c->core->r.domain[1];
   return ENTERP_OK;
 }
 

@@ -14,6 +14,7 @@ namespace enterp {
 constexpr int MAX_LEVELS = 7;     // 32^7 > 2^31 searched knots
 constexpr int MAX_DYN_DEGREE = 63;  // runtime-degree de Boor keeps its workspace in local memory
 constexpr int MAX_DYN_BEZIER = 256;
+constexpr int MAX_PRE = 4;   // nested input adaptors carried to the device
 constexpr int BLOCK = 256;
 constexpr int MAX_BLOCK = 1024;        // kernels that stage big pivot tables run one fat CTA per SM
 constexpr unsigned SEARCH_SMEM_MAX = 160u * 1024u;  // shared-memory budget for staged pivot levels
@@ -32,8 +33,14 @@ struct CurveDev {
   uint32_t imin, imax, map0, mapL;
   int32_t map_add;
   R eq_step, eq_offset, eq_first, eq_lenm2;
-  R in_add, in_mul;
-  int has_transform;
+  // input adaptors applied to the raw parameter, outermost first (base/adaptors.rs): Clamp(lo, hi) or the
+  // affine map t * a + b of TransformInput / Slice (two roundings, never fused)
+  int n_pre;
+  int pre_kind[MAX_PRE];  // 0 clamp, 1 affine
+  R pre_a[MAX_PRE], pre_b[MAX_PRE];
+  // Linear easing of the lerp factor (easing/mod.rs, plateau.rs)
+  int easing, easing_n;
+  R ease_min, ease_max;
   int coop_search;              // ablation switch: warp-cooperative instead of per-thread pivot search
   unsigned long long* invalid;  // device counter: samples where the reference would panic
 };
@@ -76,6 +83,55 @@ __device__ __forceinline__ double qnan(double) { return __longlong_as_double(0x7
 template <class R>
 __device__ __forceinline__ R merge1(R a, R b, R f, R omf) {
   return xadd(xmul(a, omf), xmul(b, f));
+}
+
+// ---- input adaptors and easing ---------------------------------------------------------------------
+// Clamp::eval: num_traits::clamp (x < min -> min, x > max -> max, NaN passes) (adaptors.rs:26-32);
+// TransformInput::eval: input * multiplication + addition (adaptors.rs:141-152).
+template <class R>
+__device__ __forceinline__ R apply_pre(const CurveDev<R>& c, R x) {
+#pragma unroll
+  for (int i = 0; i < MAX_PRE; ++i) {
+    if (i < c.n_pre) {
+      if (c.pre_kind[i] == 0)
+        x = x < c.pre_a[i] ? c.pre_a[i] : (x > c.pre_b[i] ? c.pre_b[i] : x);
+      else
+        x = xadd(xmul(x, c.pre_a[i]), c.pre_b[i]);
+    }
+  }
+  return x;
+}
+
+// easing/mod.rs:86-132: flip = 1 - x; smoothstart<N> = x^N by repeated multiplication; smoothend<N> =
+// flip(smoothstart<N>(flip(x))); smoothstep = x*x*(3 - 2*x); smootherstep = x*x*x*(x*(x*6 - 15) + 10);
+// Plateau (plateau.rs:27-48) = smoothstep(over_clamp(x, min, max)). Rust evaluates left to right.
+template <class R>
+__device__ __forceinline__ R smoothstep_exact(R x) {
+  return xmul(xmul(x, x), xsub(R(3), xmul(R(2), x)));
+}
+template <class R>
+__device__ __forceinline__ R smoothstart_exact(R x, int n) {
+  R m = x;
+  for (int i = 1; i < n; ++i) m = xmul(m, x);
+  return m;
+}
+template <class R>
+__device__ __forceinline__ R apply_easing(const CurveDev<R>& c, R f) {
+  switch (c.easing) {
+    case 1: return xsub(R(1), f);
+    case 2: return smoothstart_exact(f, c.easing_n);
+    case 3: return xsub(R(1), smoothstart_exact(xsub(R(1), f), c.easing_n));
+    case 4: return smoothstep_exact(f);
+    case 5: return xmul(xmul(xmul(f, f), f), xadd(xmul(f, xsub(xmul(f, R(6)), R(15))), R(10)));
+    case 6: {
+      R t;
+      if (f < c.ease_min) t = R(0);
+      else if (f > c.ease_max) t = R(1);
+      else t = xdiv(xsub(f, c.ease_min), xsub(c.ease_max, c.ease_min));
+      return smoothstep_exact(t);
+    }
+    default: return f;
+  }
 }
 
 // ---- sample parameter --------------------------------------------------------------------------
@@ -355,7 +411,7 @@ __global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(
        base += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long i = base + threadIdx.x;
     const bool active = i < s.count;
-    R x = active ? sample_param(s, i) : c.eq_first;
+    R x = active ? apply_pre(c, sample_param(s, i)) : c.eq_first;
     uint32_t index;
     bool valid = bspline_span<R, EQUI>(c, x, index, top);
     if (!active) continue;
@@ -411,11 +467,12 @@ __global__ void __launch_bounds__(MAX_BLOCK) linear_kernel(const CurveDev<R> c, 
        base += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long i = base + threadIdx.x;
     const bool active = i < s.count;
-    R x = active ? sample_param(s, i) : R(0);
+    R x = active ? apply_pre(c, sample_param(s, i)) : R(0);
     uint32_t imin, imax;
     R f;
     const bool valid = linear_border<R, EQUI>(c, x, imin, imax, f, top);
     if (!active) continue;
+    if (c.easing) f = apply_easing(c, f);  // easing.eval(factor), linear/mod.rs:127
     const R omf = xsub(R(1), f);
     R w[DH];
     const R* __restrict__ a = c.elems + (size_t)imin * DH;
@@ -437,8 +494,7 @@ __global__ void __launch_bounds__(BLOCK) bezier_kernel(const CurveDev<R> c, cons
   const int n = N > 0 ? N : (int)c.n_elem;
   for (unsigned long long i = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; i < s.count;
        i += (unsigned long long)gridDim.x * BLOCK) {
-    R x = sample_param(s, i);
-    if (c.has_transform) x = xadd(xmul(x, c.in_mul), c.in_add);  // TransformInput::eval (adaptors.rs:141-152)
+    const R x = apply_pre(c, sample_param(s, i));  // Bezier .domain(a,b) arrives as an affine adaptor
     const R omx = xsub(R(1), x);
     R ws[N_CAP * DH];
     if (N > 0) {
@@ -514,7 +570,7 @@ __global__ void __launch_bounds__(BLOCK) span_kernel(const CurveDev<R> c, const 
        base += (unsigned long long)gridDim.x * BLOCK) {
     const unsigned long long i = base + threadIdx.x;
     const bool active = i < s.count;
-    R x = active ? sample_param(s, i) : R(0);
+    R x = active ? apply_pre(c, sample_param(s, i)) : R(0);
     uint32_t index = 0;
     R f = R(0);
     bool valid = true;

@@ -71,6 +71,9 @@ Fail check_knots(const enterp_curve_desc& d, Shape& s) {
   if (d.knot_base == ENTERP_KNOTS_SORTED && k >= (1ull << 31)) return fail(ENTERP_UNSUPPORTED);
   if (d.kind == ENTERP_LINEAR) {
     s.degree = 1;
+    if (d.easing < ENTERP_EASE_IDENTITY || d.easing > ENTERP_EASE_PLATEAU) return fail(ENTERP_INVALID_ARGUMENT);
+    if ((d.easing == ENTERP_EASE_SMOOTHSTART || d.easing == ENTERP_EASE_SMOOTHEND) && d.easing_n < 1)
+      return fail(ENTERP_INVALID_ARGUMENT);
     if (d.knot_base == ENTERP_KNOTS_SORTED) {
       // src/linear/builder.rs:331 (count) then 335 (Sorted::new)
       if (k != e) return fail(ENTERP_KNOT_ELEMENT_INEQUALITY, e, k);
@@ -439,6 +442,16 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
   }
 
   if (d.kind == ENTERP_BSPLINE) build_rows<R>(d, s, r, vk);
+  if (d.kind == ENTERP_LINEAR) {
+    r.easing = d.easing;
+    r.easing_n = d.easing_n;
+    if (d.easing == ENTERP_EASE_PLATEAU) {
+      // Plateau::new (easing/plateau.rs:19-25): halfed = strength / 2; min = 0 + halfed; max = 1 - halfed
+      const R halfed = (R)d.easing_param / R(2);
+      r.ease_min = R(0) + halfed;
+      r.ease_max = R(1) - halfed;
+    }
+  }
 }
 
 }  // namespace

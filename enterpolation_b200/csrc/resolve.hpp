@@ -51,6 +51,9 @@ struct Resolved {
   // Bezier TransformInput (base/adaptors.rs:137-139)
   int32_t has_transform = 0;
   double in_add = 0, in_mul = 1;
+  // Linear easing (easing/mod.rs:86-132, plateau.rs): kind, N of smoothstart/smoothend, Plateau min/max in R
+  int32_t easing = 0, easing_n = 0;
+  double ease_min = 0, ease_max = 1;
   // span-row table of the fast B-spline kernel (rows.cuh / rows_layout.hpp); rows_mode 0 = none,
   // 1 = every reachable denominator is a power of two (exact inverse multiply), 2 = exact division
   // from tabulated reciprocals.

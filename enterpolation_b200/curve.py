@@ -38,15 +38,18 @@ class Curve:
     Mirrors `impl Signal<R> + Curve<R>` of Linear / Bezier / BSpline / Weighted<..>.
     """
 
-    def __init__(self, desc_arrays: _abi.DescArrays, device: int = 0):
+    def __init__(self, desc_arrays: _abi.DescArrays | None, device: int = 0, _handle=None):
         self._lib = _abi.load_library()
         self._da = desc_arrays
-        h = C.c_void_p()
-        info = _abi.ErrorInfo()
-        st = self._lib.enterp_curve_create(C.byref(desc_arrays.desc), C.byref(h), C.byref(info))
-        if st != _abi.OK:
-            info.status = st
-            raise from_info(info)
+        if _handle is not None:
+            h = _handle
+        else:
+            h = C.c_void_p()
+            info = _abi.ErrorInfo()
+            st = self._lib.enterp_curve_create(C.byref(desc_arrays.desc), C.byref(h), C.byref(info))
+            if st != _abi.OK:
+                info.status = st
+                raise from_info(info)
         self._h = h
         ci = _abi.CurveInfo()
         _check(self._lib, self._lib.enterp_curve_get_info(h, C.byref(ci)))
@@ -73,6 +76,20 @@ class Curve:
     @property
     def degree(self) -> int:
         return int(self.info.degree)
+
+    def clamp(self) -> "Curve":
+        """`Curve::clamp()` (signal.rs:271-290 -> Clamp, adaptors.rs:14-44): parameters are clamped to the
+        domain before evaluation. The new curve shares this one's device tables."""
+        h = C.c_void_p()
+        _check(self._lib, self._lib.enterp_curve_clamp(self._h, C.byref(h)))
+        return Curve(None, device=self.device, _handle=h)
+
+    def slice(self, start=None, end=None) -> "Curve":
+        """`Curve::slice(start..end)` (signal.rs:241-262 -> Slice, adaptors.rs:55-106); None = unbounded."""
+        h = C.c_void_p()
+        _check(self._lib, self._lib.enterp_curve_slice(self._h, start is not None, float(start or 0.0),
+                                                       end is not None, float(end or 0.0), C.byref(h)))
+        return Curve(None, device=self.device, _handle=h)
 
     def take(self, samples: int) -> "Take":
         """`Curve::take(samples)`: `samples` equidistant parameters over the domain (signal.rs:221-228)."""

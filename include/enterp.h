@@ -74,6 +74,10 @@ enum { ENTERP_EQ_BY_DEGREE = 0, ENTERP_EQ_BY_QUANTITY = 1 };                   /
 enum { ENTERP_EQ_DOMAIN = 0, ENTERP_EQ_NORMALIZED = 1, ENTERP_EQ_DISTANCE = 2 }; /* desc.eq_form */
 enum { ENTERP_SPACE_CONSTANT = 0, ENTERP_SPACE_DYNAMIC = 1, ENTERP_SPACE_WORKSPACE = 2 }; /* desc.space */
 enum { ENTERP_INPUT_NORMALIZED = 0, ENTERP_INPUT_DOMAIN = 1 };                 /* desc.input_form (Bezier) */
+/* desc.easing (Linear): the built-in easing functions of src/easing/mod.rs:86-132 and plateau.rs:10-57
+ * applied to the lerp factor (linear/mod.rs:127). Arbitrary closures (FuncEase) cannot cross to the device. */
+enum { ENTERP_EASE_IDENTITY = 0, ENTERP_EASE_FLIP = 1, ENTERP_EASE_SMOOTHSTART = 2, ENTERP_EASE_SMOOTHEND = 3,
+       ENTERP_EASE_SMOOTHSTEP = 4, ENTERP_EASE_SMOOTHERSTEP = 5, ENTERP_EASE_PLATEAU = 6 };
 
 /* One descriptor == one finished builder chain. The fields mirror the typestate the reference's
  * builders resolve to; validation happens in the order the builder methods are called in
@@ -101,6 +105,10 @@ typedef struct enterp_curve_desc {
   int32_t input_form;   /* Bezier: .normalized::<R>() | .domain(in_a, in_b) (TransformInput) */
   uint64_t workspace_n; /* N of constant::<N>() / S.len() of workspace(S); ignored for dynamic */
   double in_a, in_b;
+
+  int32_t easing;       /* Linear: .easing(F), one of ENTERP_EASE_* (default identity) */
+  int32_t easing_n;     /* N of smoothstart::<R, N> / smoothend::<R, N> (>= 1) */
+  double easing_param;  /* strength of Plateau::new(strength) */
 } enterp_curve_desc;
 
 /* Payload of the reference's error structs (found/necessary, elements/knots, index, degree). */
@@ -144,6 +152,14 @@ ENTERP_API enterp_status enterp_curve_get_info(const enterp_curve* curve, enterp
 /* Curve::domain(): linear/mod.rs:139-141, bspline/mod.rs:180-185, bezier/mod.rs:257-259,
  * base/adaptors.rs:161-166 (TransformInput). */
 ENTERP_API enterp_status enterp_curve_domain(const enterp_curve* curve, double out[2]);
+/* Curve::clamp() (src/base/signal.rs:271-290 -> Clamp, src/base/adaptors.rs:14-44): a new handle that
+ * clamps the parameter to `base`'s domain before evaluating; shares base's tables. domain() is unchanged. */
+ENTERP_API enterp_status enterp_curve_clamp(const enterp_curve* base, enterp_curve** out);
+/* Curve::slice(bounds) (signal.rs:241-262 -> Slice, adaptors.rs:55-106): the parameter is mapped by
+ * t * scale + (start - domain_start), scale = (end - start) / (domain_end - domain_start); an absent bound
+ * (has_* == 0) defaults to the domain's. domain() is reported as the base's (adaptors.rs:99-105). */
+ENTERP_API enterp_status enterp_curve_slice(const enterp_curve* base, int has_start, double start, int has_end,
+                                            double end, enterp_curve** out);
 /* Replicates the resolved tables onto `device` ("uploaded once"). Implicit on first eval. */
 ENTERP_API enterp_status enterp_curve_upload(enterp_curve* curve, int device);
 

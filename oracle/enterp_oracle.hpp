@@ -344,18 +344,62 @@ struct DynSpace {
 // ---------------------------------------------------------------------------------------------
 // Curves
 // ---------------------------------------------------------------------------------------------
-// linear/mod.rs:122-128 (eval), 139-141 (domain); easing = Identity (easing/mod.rs:67-72).
+// Built-in easing functions (easing/mod.rs:67-72 Identity, 86-132 flip/smoothstart/smoothend/smoothstep/
+// smootherstep; easing/plateau.rs:10-57 Plateau). One runtime-tagged struct stands for the `F` parameter.
+template <class R>
+struct Easing {
+  int kind = 0;  // ENTERP_EASE_*: 0 identity, 1 flip, 2 smoothstart<N>, 3 smoothend<N>, 4 smoothstep, 5 smootherstep, 6 plateau
+  int n = 1;
+  R min = R(0), max = R(1);  // Plateau
+  static Easing plateau(R strength) {  // plateau.rs:19-25
+    Easing e;
+    e.kind = 6;
+    const R halfed = strength / from_usize<R>(2);
+    e.min = R(0) + halfed;
+    e.max = R(1) - halfed;
+    return e;
+  }
+  static R flip(R x) { return R(1) - x; }                       // mod.rs:86-91
+  static R smoothstart(R x, int n) {                            // mod.rs:93-102
+    R mul = x;
+    for (int i = 1; i < n; ++i) mul = mul * x;
+    return mul;
+  }
+  static R smoothstep(R x) { return x * x * (from_usize<R>(3) - from_usize<R>(2) * x); }  // mod.rs:114-121
+  static R smootherstep(R x) {                                  // mod.rs:123-132
+    return x * x * x * (x * (x * from_usize<R>(6) - from_usize<R>(15)) + from_usize<R>(10));
+  }
+  static R over_clamp(R input, R min, R max) {                  // plateau.rs:27-38
+    if (input < min) return R(0);
+    if (input > max) return R(1);
+    return (input - min) / (max - min);
+  }
+  R eval(R x) const {
+    switch (kind) {
+      case 1: return flip(x);
+      case 2: return smoothstart(x, n);
+      case 3: return flip(smoothstart(flip(x), n));             // mod.rs:104-112
+      case 4: return smoothstep(x);
+      case 5: return smootherstep(x);
+      case 6: return smoothstep(over_clamp(x, min, max));       // plateau.rs:45-47
+      default: return x;
+    }
+  }
+};
+
+// linear/mod.rs:122-128 (eval), 139-141 (domain).
 template <class K, class E>
 struct Linear {
   using R = typename K::Output;
   using Output = typename E::Output;
   K knots;
   E elements;
+  Easing<R> easing;
   Output eval(R scalar) const {
     Border<R> b = knots.upper_border(scalar);
     Output min_point = elements.eval(b.min_index);
     Output max_point = elements.eval(b.max_index);
-    return merge(min_point, max_point, b.factor);
+    return merge(min_point, max_point, easing.eval(b.factor));
   }
   void domain(R out[2]) const {
     out[0] = knots.first();

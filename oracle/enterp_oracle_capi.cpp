@@ -50,6 +50,8 @@ struct Resolved {
   size_t space_len = 0;
   int input_form = 0;
   double in_a = 0, in_b = 0;
+  int easing = 0, easing_n = 1;
+  double easing_param = 0;
 };
 
 template <class R>
@@ -97,6 +99,12 @@ Err resolve(const enterp_curve_desc& d, Resolved& r) {
         return err(ENTERP_INVALID_ARGUMENT);
       }
       r.degree = 1;
+      if (d.easing < ENTERP_EASE_IDENTITY || d.easing > ENTERP_EASE_PLATEAU) return err(ENTERP_INVALID_ARGUMENT);
+      if ((d.easing == ENTERP_EASE_SMOOTHSTART || d.easing == ENTERP_EASE_SMOOTHEND) && d.easing_n < 1)
+        return err(ENTERP_INVALID_ARGUMENT);
+      r.easing = d.easing;
+      r.easing_n = d.easing_n;
+      r.easing_param = d.easing_param;
       return Err{};
     }
     case ENTERP_BEZIER: {
@@ -348,6 +356,65 @@ struct CurveImpl final : CurveIface {
   }
 };
 
+// Clamp<G> (base/adaptors.rs:14-44) and Slice<G, R> (55-106) over an already built curve. The adaptor only
+// rewrites the parameter, so it is applied to the parameter array before the wrapped curve evaluates it.
+struct Adapted final : CurveIface {
+  const CurveIface* inner;
+  int op;         // 0 clamp, 1 slice
+  double a, b;    // clamp: [min, max] = inner domain; slice: multiplication, addition (exact R values)
+  Adapted(const CurveIface* in, int op_, double a_, double b_) : inner(in), op(op_), a(a_), b(b_) { res = in->res; }
+  void domain(double out[2]) const override { inner->domain(out); }  // Clamp 40-43; Slice 99-105
+  template <class R>
+  R map(R x) const {
+    if (op == 0) {  // num_traits::clamp
+      const R lo = (R)a, hi = (R)b;
+      if (x < lo) return lo;
+      if (x > hi) return hi;
+      return x;
+    }
+    return x * (R)a + (R)b;  // TransformInput::eval (adaptors.rs:141-152)
+  }
+  std::vector<unsigned char> mapped(const void* t, size_t n) const {
+    const size_t rs = res.scalar == ENTERP_F32 ? 4 : 8;
+    std::vector<unsigned char> buf(n * rs);
+    if (res.scalar == ENTERP_F32)
+      for (size_t i = 0; i < n; ++i) ((float*)buf.data())[i] = map<float>(((const float*)t)[i]);
+    else
+      for (size_t i = 0; i < n; ++i) ((double*)buf.data())[i] = map<double>(((const double*)t)[i]);
+    return buf;
+  }
+  std::vector<unsigned char> stepped(size_t n_total, size_t first, size_t count) const {
+    double d[2];
+    domain(d);
+    const size_t rs = res.scalar == ENTERP_F32 ? 4 : 8;
+    std::vector<unsigned char> buf(count * rs);
+    if (res.scalar == ENTERP_F32) {
+      Stepper<float> st(n_total, (float)d[0], (float)d[1]);
+      for (size_t i = 0; i < count; ++i) ((float*)buf.data())[i] = st.at(first + i);
+    } else {
+      Stepper<double> st(n_total, d[0], d[1]);
+      for (size_t i = 0; i < count; ++i) ((double*)buf.data())[i] = st.at(first + i);
+    }
+    return buf;
+  }
+  uint64_t eval_many(const void* t, size_t n, void* out) const override {
+    auto m = mapped(t, n);
+    return inner->eval_many(m.data(), n, out);
+  }
+  uint64_t take(size_t n_total, size_t first, size_t count, void* out) const override {
+    auto t = stepped(n_total, first, count);  // Curve::take over the adaptor's own domain()
+    return eval_many(t.data(), count, out);
+  }
+  uint64_t span_many(const void* t, size_t n, uint32_t* idx, void* factor) const override {
+    auto m = mapped(t, n);
+    return inner->span_many(m.data(), n, idx, factor);
+  }
+  uint64_t span_take(size_t n_total, size_t first, size_t count, uint32_t* idx, void* factor) const override {
+    auto t = stepped(n_total, first, count);
+    return span_many(t.data(), count, idx, factor);
+  }
+};
+
 template <class R, int D, class C>
 CurveIface* finish(const C& c) {
   return new CurveImpl<C, R, D>(c);
@@ -414,10 +481,17 @@ CurveIface* build_typed(const enterp_curve_desc& d, const Resolved& r) {
 
   CurveIface* out = nullptr;
   if (r.kind == ENTERP_LINEAR) {
+    Easing<R> ease;
+    if (r.easing == ENTERP_EASE_PLATEAU) {
+      ease = Easing<R>::plateau((R)r.easing_param);
+    } else {
+      ease.kind = r.easing;
+      ease.n = r.easing_n;
+    }
     if (r.knot_base == ENTERP_KNOTS_SORTED)
-      out = wrap<R, D, W>(r, Linear<Sorted<R>, EChain>{Sorted<R>(kn, r.inner_len), elems});
+      out = wrap<R, D, W>(r, Linear<Sorted<R>, EChain>{Sorted<R>(kn, r.inner_len), elems, ease});
     else
-      out = wrap<R, D, W>(r, Linear<Equidistant<R>, EChain>{make_equidistant<R>(r), elems});
+      out = wrap<R, D, W>(r, Linear<Equidistant<R>, EChain>{make_equidistant<R>(r), elems, ease});
   } else if (r.kind == ENTERP_BEZIER) {
     out = with_space<Elem>(r, r.e, [&](auto space) {
       return wrap<R, D, W>(r, Bezier<R, EChain, decltype(space)>{elems, space});
@@ -503,6 +577,33 @@ ORA_API int ora_create(const enterp_curve_desc* desc, void** out, enterp_error_i
   return ENTERP_OK;
 }
 ORA_API void ora_destroy(void* c) { delete static_cast<CurveIface*>(c); }
+// Curve::clamp() / Curve::slice(bounds). The caller keeps `base` alive for the lifetime of the result.
+ORA_API void* ora_clamp(void* base) {
+  const CurveIface* b = static_cast<const CurveIface*>(base);
+  double d[2];
+  b->domain(d);
+  return new Adapted(b, 0, d[0], d[1]);
+}
+ORA_API void* ora_slice(void* base, int has_start, double start, int has_end, double end) {
+  const CurveIface* b = static_cast<const CurveIface*>(base);
+  double d[2];
+  b->domain(d);
+  double mul, add;
+  if (b->res.scalar == ENTERP_F32) {  // Slice::new, adaptors.rs:61-81, in R arithmetic
+    const float s0 = (float)d[0], s1 = (float)d[1];
+    const float b0 = has_start ? (float)start : s0, b1 = has_end ? (float)end : s1;
+    const float scale = (b1 - b0) / (s1 - s0);
+    mul = scale;
+    add = b0 - s0;
+  } else {
+    const double s0 = d[0], s1 = d[1];
+    const double b0 = has_start ? start : s0, b1 = has_end ? end : s1;
+    const double scale = (b1 - b0) / (s1 - s0);
+    mul = scale;
+    add = b0 - s0;
+  }
+  return new Adapted(b, 1, mul, add);
+}
 ORA_API void ora_domain(void* c, double out[2]) { static_cast<CurveIface*>(c)->domain(out); }
 ORA_API void ora_info(void* c, enterp_curve_info* info) {
   const Resolved& r = static_cast<CurveIface*>(c)->res;

@@ -41,6 +41,10 @@ def lib() -> C.CDLL:
     L.ora_create.restype = C.c_int
     L.ora_destroy.argtypes = [vp]
     L.ora_destroy.restype = None
+    L.ora_clamp.argtypes = [vp]
+    L.ora_clamp.restype = vp
+    L.ora_slice.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_double]
+    L.ora_slice.restype = vp
     L.ora_domain.argtypes = [vp, C.POINTER(C.c_double * 2)]
     L.ora_domain.restype = None
     L.ora_info.argtypes = [vp, C.POINTER(_abi.CurveInfo)]
@@ -81,8 +85,14 @@ class OracleError(Exception):
 class OracleCurve:
     """A curve built by the oracle from the same descriptor the product consumes."""
 
-    def __init__(self, da: _abi.DescArrays):
+    def __init__(self, da: _abi.DescArrays, _handle=None, _base=None):
         self._da = da
+        self._base = _base  # adaptors keep the wrapped curve alive
+        if _handle is not None:
+            self._h = C.c_void_p(_handle)
+            self.scalar, self.dim = _base.scalar, _base.dim
+            self.dtype = _abi.NP_DTYPE[self.scalar]
+            return
         h = C.c_void_p()
         info = _abi.ErrorInfo()
         st = lib().ora_create(C.byref(da.desc), C.byref(h), C.byref(info))
@@ -99,6 +109,15 @@ class OracleCurve:
         if h and _lib is not None:
             _lib.ora_destroy(h)
             self._h = None
+
+    def clamp(self) -> "OracleCurve":
+        """Curve::clamp() (signal.rs:271-290)."""
+        return OracleCurve(None, _handle=lib().ora_clamp(self._h), _base=self)
+
+    def slice(self, start=None, end=None) -> "OracleCurve":
+        """Curve::slice(start..end) (signal.rs:241-262); None = unbounded."""
+        h = lib().ora_slice(self._h, start is not None, float(start or 0.0), end is not None, float(end or 0.0))
+        return OracleCurve(None, _handle=h, _base=self)
 
     def domain(self):
         d = (C.c_double * 2)()

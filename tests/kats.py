@@ -153,5 +153,21 @@ kat(name="nurbs_circle_quadrants", src="examples/nurbs.rs:112-117 (assert_float_
     expect=[[math.cos(v * 0.5 * math.pi), math.sin(v * 0.5 * math.pi)] for v in range(5)], ulps=None, abs=1e-6)
 
 
+# ---- adaptors and easings ------------------------------------------------
+def _lin_012():
+    return Linear.builder().elements([0.0, 5.0, 3.0]).knots([0.0, 1.0, 2.0])
+
+
+kat(name="curve_slice_doc", src="src/base/signal.rs:241-249",
+    make=_lin_012, adapt=lambda c: c.slice(0.5, 1.5), take=3, expect=[2.5, 5.0, 4.0], ulps=4)
+kat(name="curve_clamp_doc", src="src/base/signal.rs:271-279",
+    make=lambda: Linear.builder().elements([0.0, 3.0]).knots([0.0, 1.0]), adapt=lambda c: c.clamp(),
+    sample=[-1.0, 0.0, 0.5, 1.0, 2.0], expect=[0.0, 0.0, 1.5, 3.0, 3.0], ulps=4)
+# adaptors.rs:359-368 slices the Identity curve over [0,1] to 10..100; Identity is the degree-1 curve 0 -> 1
+kat(name="adaptors_slice_test", src="src/base/adaptors.rs:359-368",
+    make=lambda: Linear.builder().elements([0.0, 1.0]).knots([0.0, 1.0]), adapt=lambda c: c.slice(10.0, 100.0),
+    sample=[0.0, 1.0], expect=[10.0, 100.0], ulps=4)
+
+
 def all_kats():
     return KATS

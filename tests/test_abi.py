@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_desc_layout_matches_header():
     # field order/types are the ABI; sizes are what a C compiler produces for the header's struct
-    assert C.sizeof(_abi.CurveDesc) == 128
+    assert C.sizeof(_abi.CurveDesc) == 144
     assert C.sizeof(_abi.ErrorInfo) == 32
     assert C.sizeof(_abi.CurveInfo) == 72
 

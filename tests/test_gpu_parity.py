@@ -238,3 +238,65 @@ def test_config_shapes_small():
         for first in (0, (1 << 31) - 50_000, (1 << 32) - 100_000):
             assert_bits_equal(c.take_device(1 << 32, first, 100_000).cpu().numpy(), ref.take(1 << 32, first, 100_000, threads=8),
                               f"C5 stops={stops} first={first}")
+
+
+# ---- input adaptors and built-in easings ---------------------------------------
+def check_adapted(curve, ref, t, what, take_n=333):
+    tt = torch.from_numpy(np.ascontiguousarray(t)).cuda()
+    assert_bits_equal(curve.sample_device(tt).cpu().numpy(), ref.eval(t), what + " batch")
+    assert_bits_equal(curve.take_device(take_n).cpu().numpy(), ref.take(take_n), what + " take")
+    assert_bits_equal(np.asarray(curve.take(take_n).collect()), ref.take(take_n), what + " take_host")
+    idx, fac = curve.span_device(tt)
+    widx, wfac = ref.span(t)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32), widx), what + " span"
+    assert [float(x) for x in curve.domain()] == [float(x) for x in ref.domain()], what + " domain"
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+def test_clamp_and_slice_adaptors(scalar):
+    from enterpolation_b200 import easing as E  # noqa: F401
+    dtype = DT[scalar]
+    rng = np.random.default_rng(3)
+    el = rand_elements(9, 3, dtype, 0x51)
+    builders = {
+        "bspline_equi": BSpline.builder().clamped().elements(el).equidistant(scalar).degree(3).domain(-1.0, 2.0).constant(4),
+        "bspline_sorted": BSpline.builder().elements(el).knots(sorted_knots(10, dtype, 0x52)).constant(3),
+        "linear": Linear.builder().elements(el).knots(sorted_knots(9, dtype, 0x53)),
+        "bezier_dom": Bezier.builder().elements(el).domain(0.0, 2.0, scalar).constant(),
+        "nurbs": BSpline.builder().elements_with_weights(el, (0.5 + u01(9, 0x54, dtype)).astype(dtype)).equidistant(scalar)
+        .degree(2).normalized().dynamic(),
+    }
+    for name, b in builders.items():
+        base, rbase = b.build(), oracle.OracleCurve(b.to_desc())
+        d = rbase.domain()
+        lo, hi = float(d[0]), float(d[1])
+        t = adversarial(np.linspace(lo, hi, 9), dtype, rng, n_random=800)
+        mid0, mid1 = lo + 0.25 * (hi - lo), lo + 0.6 * (hi - lo)
+        check_adapted(base.clamp(), rbase.clamp(), t, f"{name} clamp {scalar}")
+        check_adapted(base.slice(mid0, mid1), rbase.slice(mid0, mid1), t, f"{name} slice {scalar}")
+        check_adapted(base.slice(None, mid1), rbase.slice(None, mid1), t, f"{name} slice-open {scalar}")
+        # nesting: clamp of a slice, slice of a clamp
+        check_adapted(base.slice(mid0, mid1).clamp(), rbase.slice(mid0, mid1).clamp(), t, f"{name} slice.clamp {scalar}")
+        check_adapted(base.clamp().slice(mid0, mid1), rbase.clamp().slice(mid0, mid1), t, f"{name} clamp.slice {scalar}")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("knots_kind", ["sorted", "equidistant"])
+def test_linear_easings(scalar, knots_kind):
+    from enterpolation_b200 import easing as E
+    dtype = DT[scalar]
+    rng = np.random.default_rng(5)
+    el = rand_elements(6, 2, dtype, 0x61)
+    easings = [E.Identity(), E.flip, E.smoothstart(1), E.smoothstart(2), E.smoothstart(5), E.smoothend(2), E.smoothend(3),
+               E.smoothstep, E.smootherstep, E.Plateau(0.7), E.Plateau(0.0), E.Plateau(1.0)]
+    for ez in easings:
+        b = Linear.builder().elements(el)
+        if knots_kind == "sorted":
+            kn = sorted_knots(6, dtype, 0x62)
+            b = b.knots(kn)
+            t = adversarial(kn, dtype, rng, n_random=1500)
+        else:
+            b = b.equidistant(scalar).domain(-1.0, 1.0)  # examples/plateaus.rs:35-41
+            t = adversarial(np.linspace(-1.0, 1.0, 21), dtype, rng, n_random=1500)
+        b = b.easing(ez)
+        check_adapted(b.build(), oracle.OracleCurve(b.to_desc()), t, f"easing {ez} {knots_kind} {scalar}")
