@@ -29,7 +29,7 @@ CUDA_ERROR = 13
 LINEAR, BEZIER, BSPLINE = 0, 1, 2
 F32, F64 = 0, 1
 OPEN, CLAMPED, LEGACY = 0, 1, 2
-KNOTS_SORTED, KNOTS_EQUIDISTANT = 0, 1
+KNOTS_SORTED, KNOTS_EQUIDISTANT, KNOTS_CONST_EQUIDISTANT = 0, 1, 2
 EQ_BY_DEGREE, EQ_BY_QUANTITY = 0, 1
 EQ_DOMAIN, EQ_NORMALIZED, EQ_DISTANCE = 0, 1, 2
 SPACE_CONSTANT, SPACE_DYNAMIC, SPACE_WORKSPACE = 0, 1, 2
@@ -160,7 +160,8 @@ class DescArrays:
 
 
 def make_desc(kind, scalar, elements, weights=None, *, mode=OPEN, knots=None, equidistant=None,
-              space=(SPACE_DYNAMIC, 0), bezier_domain=None, easing=(EASE_IDENTITY, 0, 0.0)) -> DescArrays:
+              space=(SPACE_DYNAMIC, 0), bezier_domain=None, easing=(EASE_IDENTITY, 0, 0.0),
+              const_equidistant=False) -> DescArrays:
     """Flatten one finished builder chain into the C descriptor.
 
     elements: array-like [n] or [n][dim]; weights: [n] or None; knots: [k] or None;
@@ -198,6 +199,8 @@ def make_desc(kind, scalar, elements, weights=None, *, mode=OPEN, knots=None, eq
         d.knot_base = KNOTS_EQUIDISTANT
         d.eq_by, d.eq_count, d.eq_form, a, b = equidistant
         d.eq_a, d.eq_b = float(dt(a)), float(dt(b))
+    elif const_equidistant:
+        d.knot_base = KNOTS_CONST_EQUIDISTANT
     else:
         d.knot_base = KNOTS_SORTED if kind != BEZIER else 0
     d.space, d.workspace_n = space

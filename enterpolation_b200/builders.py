@@ -64,6 +64,7 @@ class _Chain:
         self._space = (_abi.SPACE_DYNAMIC, 0)
         self._bezier_domain = None
         self._easing = (_abi.EASE_IDENTITY, 0, 0.0)
+        self._const_equidistant = False
         self._device = 0
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -83,7 +84,8 @@ class _Chain:
         return _abi.make_desc(self._kind, self._resolved_scalar(),
                               [] if self._elements is None else self._elements, self._weights,
                               mode=self._mode, knots=self._knots, equidistant=eq, space=self._space,
-                              bezier_domain=self._bezier_domain, easing=self._easing)
+                              bezier_domain=self._bezier_domain, easing=self._easing,
+                              const_equidistant=self._const_equidistant)
 
     def _validate(self, stage: int):
         """Ask the C library whether the chain so far is valid (Director semantics)."""
@@ -273,6 +275,16 @@ class Linear:
     @staticmethod
     def builder() -> LinearBuilder:
         return LinearBuilder(immediate=False)
+
+    @staticmethod
+    def equidistant_unchecked(elements, scalar="f64") -> LinearBuilder:
+        """`Linear::equidistant_unchecked(elements)` / `ConstEquidistantLinear` (linear/mod.rs:193-216): knots
+        i/(N-1) on [0,1] with ConstEquidistant's own arithmetic (list.rs:566-721). Returns a chain whose
+        `.build()` yields the curve (and whose `.to_desc()` feeds the oracle)."""
+        b = LinearBuilder(immediate=False)
+        b._scalar = _scalar_of(scalar)
+        b._const_equidistant = True
+        return b.elements(elements)
 
     @staticmethod
     def director() -> LinearBuilder:

@@ -244,6 +244,7 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   d.eq_offset = (R)r.eq_offset;
   d.eq_first = (R)r.eq_first;
   d.eq_lenm2 = r.inner_len >= 2 ? (R)(r.inner_len - 2) : R(0);  // from_usize(len - 2), list.rs:546
+  d.eq_const = r.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT ? 1 : 0;
   d.n_pre = (int)cv.pre.size();
   for (int i = 0; i < d.n_pre && i < MAX_PRE; ++i) {
     d.pre_kind[i] = cv.pre[i].kind;
@@ -290,7 +291,7 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
   const CurveDev<R> d = make_dev<R>(cv, rp);
   const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 16u) == 0;
   const bool proj = r.weighted != 0;
-  const bool equi = r.knot_base == ENTERP_KNOTS_EQUIDISTANT;
+  const bool equi = r.knot_base != ENTERP_KNOTS_SORTED;
   cudaError_t e;
   switch (r.kind) {
     case ENTERP_BSPLINE: {
@@ -362,7 +363,7 @@ enterp_status span_common(enterp_curve* c, int device, bool take, const void* t,
   DeviceGuard g(device);
   if (!g.ok) return ENTERP_NO_DEVICE;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  const bool equi = c->core->r.knot_base == ENTERP_KNOTS_EQUIDISTANT;
+  const bool equi = c->core->r.knot_base != ENTERP_KNOTS_SORTED;
   cudaError_t e;
   if (c->core->r.scalar == ENTERP_F32) {
     auto s = take ? take_src<float>(c->core->r, n_total, first, count) : batch_src<float>(t, count);

@@ -33,6 +33,7 @@ struct CurveDev {
   uint32_t imin, imax, map0, mapL;
   int32_t map_add;
   R eq_step, eq_offset, eq_first, eq_lenm2;
+  int eq_const;  // ConstEquidistant (list.rs:566-721): scaled = x * eq_step with eq_step = fl(N-1), offset 0
   // input adaptors applied to the raw parameter, outermost first (base/adaptors.rs): Clamp(lo, hi) or the
   // affine map t * a + b of TransformInput / Slice (two roundings, never fused)
   int n_pre;
@@ -305,7 +306,8 @@ __device__ __forceinline__ bool linear_border(const CurveDev<R>& c, R x, uint32_
                                               const R* __restrict__ top = nullptr) {
   const uint32_t len = c.inner_len;
   if (EQUI) {
-    const R scaled = xdiv(xsub(x, c.eq_offset), c.eq_step);
+    // Equidistant::upper_border (list.rs:532-551) / ConstEquidistant::upper_border (702-720)
+    const R scaled = c.eq_const ? xmul(x, c.eq_step) : xdiv(xsub(x, c.eq_offset), c.eq_step);
     if (x < c.eq_offset) {
       imin = 0;
       imax = 1;

@@ -67,7 +67,12 @@ Fail check_knots(const enterp_curve_desc& d, Shape& s) {
     s.degree = e - 1;
     return ok();
   }
-  if (d.knot_base != ENTERP_KNOTS_SORTED && d.knot_base != ENTERP_KNOTS_EQUIDISTANT) return fail(ENTERP_INVALID_ARGUMENT);
+  if (d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT) {
+    // Linear::equidistant_unchecked (src/linear/mod.rs:193-207) is the only constructor over ConstEquidistant
+    if (d.kind != ENTERP_LINEAR) return fail(ENTERP_UNSUPPORTED);
+  } else if (d.knot_base != ENTERP_KNOTS_SORTED && d.knot_base != ENTERP_KNOTS_EQUIDISTANT) {
+    return fail(ENTERP_INVALID_ARGUMENT);
+  }
   if (d.knot_base == ENTERP_KNOTS_SORTED && k >= (1ull << 31)) return fail(ENTERP_UNSUPPORTED);
   if (d.kind == ENTERP_LINEAR) {
     s.degree = 1;
@@ -80,6 +85,8 @@ Fail check_knots(const enterp_curve_desc& d, Shape& s) {
       Fail f = sorted_check(d);
       if (f.status) return f;
       s.inner_len = s.virt_len = k;
+    } else if (d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT) {
+      s.inner_len = s.virt_len = e;  // ConstEquidistant<R, N> with N = elements.len()
     } else {
       // src/linear/builder.rs:427-453: as many equidistant knots as elements
       if (d.eq_form < ENTERP_EQ_DOMAIN || d.eq_form > ENTERP_EQ_DISTANCE) return fail(ENTERP_INVALID_ARGUMENT);
@@ -331,6 +338,12 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
   std::vector<R> inner(s.inner_len);
   if (d.knot_base == ENTERP_KNOTS_SORTED) {
     std::memcpy(inner.data(), d.knots, s.inner_len * sizeof(R));
+  } else if (d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT) {
+    // ConstEquidistant::eval (list.rs:588-590): fl(i) / fl(N - 1); the span code multiplies by fl(N - 1)
+    const R nm1 = (R)(s.inner_len - 1);
+    for (uint64_t i = 0; i < s.inner_len; ++i) inner[i] = (R)i / nm1;
+    r.eq_step = nm1;
+    r.eq_offset = 0;
   } else {
     // Equidistant::{new, normalized, step} (src/base/list.rs:380-408) and eval (416-418):
     // step * fl(i) + offset — two roundings per knot, exactly as recomputed upstream.

@@ -88,6 +88,10 @@ Err resolve(const enterp_curve_desc& d, Resolved& r) {
         if (s.status) return s;
         r.knot_base = ENTERP_KNOTS_SORTED;
         r.inner_len = r.virt_len = k;
+      } else if (d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT) {
+        // Linear::equidistant_unchecked (linear/mod.rs:193-207): ConstEquidistant<R, N>, N = elements.len()
+        r.knot_base = ENTERP_KNOTS_CONST_EQUIDISTANT;
+        r.inner_len = r.virt_len = e;
       } else if (d.knot_base == ENTERP_KNOTS_EQUIDISTANT) {
         // linear/builder.rs:427-453: Equidistant::{new,normalized,step}(elements.len(), ..)
         r.knot_base = ENTERP_KNOTS_EQUIDISTANT;
@@ -490,6 +494,8 @@ CurveIface* build_typed(const enterp_curve_desc& d, const Resolved& r) {
     }
     if (r.knot_base == ENTERP_KNOTS_SORTED)
       out = wrap<R, D, W>(r, Linear<Sorted<R>, EChain>{Sorted<R>(kn, r.inner_len), elems, ease});
+    else if (r.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT)
+      out = wrap<R, D, W>(r, Linear<ConstEquidistant<R>, EChain>{ConstEquidistant<R>(r.inner_len), elems, ease});
     else
       out = wrap<R, D, W>(r, Linear<Equidistant<R>, EChain>{make_equidistant<R>(r), elems, ease});
   } else if (r.kind == ENTERP_BEZIER) {

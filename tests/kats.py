@@ -118,6 +118,10 @@ kat(name="example_linear_approx", src="examples/linear.rs:9-21",
     expect=[2.0, 2.111111111111111, 2.2222222222222223, 2.3333333333333335, 2.4444444444444446,
             2.5555555555555554, 2.666666666666667, 2.7777777777777777, 2.888888888888889, 3.0], ulps=0)
 
+kat(name="linear_const_creation", src="src/linear/mod.rs:281-291 (ConstEquidistantLinear)",
+    make=lambda: Linear.equidistant_unchecked([20.0, 100.0, 0.0, 200.0], "f64"),
+    take=7, expect=_LIN7, ulps=4)
+
 # ---- Bezier values ---------------------------------------------------------------------------
 kat(name="bezier_module_doc", src="src/bezier/mod.rs:11-19",
     make=lambda: Bezier.builder().elements([0.0, 5.0, 3.0]).normalized("f64").constant(3),

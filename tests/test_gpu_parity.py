@@ -134,13 +134,21 @@ def test_bspline_equidistant(scalar, mode, form, degree, dim, weighted):
 
 @pytest.mark.parametrize("scalar", ["f32", "f64"])
 @pytest.mark.parametrize("dim,weighted", [(1, 0), (3, 0), (2, 1), (4, 1)])
-@pytest.mark.parametrize("knots_kind", ["sorted", "sorted_repeats", "domain", "normalized", "distance"])
+@pytest.mark.parametrize("knots_kind", ["sorted", "sorted_repeats", "domain", "normalized", "distance", "const"])
 def test_linear(scalar, dim, weighted, knots_kind):
     dtype = DT[scalar]
     rng = np.random.default_rng(dim)
     e = 37
     el = rand_elements(e, dim, dtype, 0xC1)
     b = Linear.builder()
+    if knots_kind == "const":  # ConstEquidistantLinear (linear/mod.rs:193-216) has no weighted constructor
+        if weighted:
+            pytest.skip("equidistant_unchecked takes plain elements")
+        b = Linear.equidistant_unchecked(el, scalar)
+        t = adversarial(np.linspace(0.0, 1.0, 4 * (e - 1) + 1), dtype, rng)
+        t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+        check_curve(b, t, what=f"linear {scalar} d{dim} const-equidistant")
+        return
     b = b.elements_with_weights(el, (0.5 + u01(e, 0xC3, dtype)).astype(dtype)) if weighted else b.elements(el)
     if knots_kind.startswith("sorted"):
         knots = sorted_knots(e, dtype, 0xC2, repeat_every=4 if knots_kind == "sorted_repeats" else 0)
