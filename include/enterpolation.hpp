@@ -105,6 +105,28 @@ class Curve {
   enterp_curve* handle() const { return h_; }
 
   Take<R> take(uint64_t samples) const { return Take<R>(this, samples, 0, samples); }  // Curve::take
+  // Curve::clamp() (signal.rs:271-290) and Curve::slice(start..end) (signal.rs:241-262): derived handles that
+  // share this curve's device tables.
+  Curve clamp() const {
+    enterp_curve* h = nullptr;
+    check(enterp_curve_clamp(h_, &h));
+    return Curve(h);
+  }
+  Curve slice(R start, R end) const {
+    enterp_curve* h = nullptr;
+    check(enterp_curve_slice(h_, 1, (double)start, 1, (double)end, &h));
+    return Curve(h);
+  }
+  Curve slice_from(R start) const {  // start..
+    enterp_curve* h = nullptr;
+    check(enterp_curve_slice(h_, 1, (double)start, 0, 0.0, &h));
+    return Curve(h);
+  }
+  Curve slice_to(R end) const {  // ..end
+    enterp_curve* h = nullptr;
+    check(enterp_curve_slice(h_, 0, 0.0, 1, (double)end, &h));
+    return Curve(h);
+  }
   std::vector<R> sample(const std::vector<R>& t, int device = 0) const {                // Signal::sample
     std::vector<R> out(t.size() * (size_t)info_.dim);
     check(enterp_sample_host(h_, device, t.data(), t.size(), out.data()));
@@ -241,6 +263,19 @@ class LinearBuilder : public BuilderBase<LinearBuilder<R>, R> {
   LinearBuilder& equidistant() {  // 362-369
     this->c_.d.knot_base = ENTERP_KNOTS_EQUIDISTANT;
     this->c_.d.eq_form = ENTERP_EQ_NORMALIZED;
+    return *this;
+  }
+  // Linear::equidistant_unchecked (src/linear/mod.rs:193-207): ConstEquidistant knots i/(N-1) on [0,1]
+  LinearBuilder& const_equidistant() {
+    this->c_.d.knot_base = ENTERP_KNOTS_CONST_EQUIDISTANT;
+    this->c_.validate(1);
+    return *this;
+  }
+  // .easing(F) (src/linear/builder.rs:496-503) for the built-in easings of src/easing/
+  LinearBuilder& easing(int ease_kind, int n = 0, R param = R(0)) {
+    this->c_.d.easing = ease_kind;
+    this->c_.d.easing_n = n;
+    this->c_.d.easing_param = param;
     return *this;
   }
   LinearBuilder& domain(R a, R b) { return form(ENTERP_EQ_DOMAIN, a, b); }      // 427-453

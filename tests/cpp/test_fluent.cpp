@@ -67,6 +67,18 @@ int main() {
   auto lin = Linear::builder<double>().elements({20.0, 100.0, 0.0, 200.0}).knots({1.0, 2.0, 3.0, 4.0}).build();
   auto v = lin.sample({1.5, 2.5, -1.0, 5.0});
   EXPECT(v[0] == 60.0 && v[1] == 50.0 && v[2] == -140.0 && v[3] == 400.0);
+  // signal.rs:271-279 clamp doctest and 241-249 slice doctest
+  auto l2 = Linear::builder<double>().elements({0.0, 3.0}).knots({0.0, 1.0}).build();
+  auto cl = l2.clamp().sample({-1.0, 0.0, 0.5, 1.0, 2.0});
+  EXPECT(cl[0] == 0.0 && cl[2] == 1.5 && cl[4] == 3.0);
+  auto l3 = Linear::builder<double>().elements({0.0, 5.0, 3.0}).knots({0.0, 1.0, 2.0}).build();
+  auto sl = l3.slice(0.5, 1.5).take(3).collect();
+  EXPECT(sl[0] == 2.5 && sl[1] == 5.0 && sl[2] == 4.0);
+  // easing + ConstEquidistantLinear (linear/mod.rs:281-291)
+  auto ce = Linear::builder<double>().elements({20.0, 100.0, 0.0, 200.0}).const_equidistant().build().take(7).collect();
+  EXPECT(ce[0] == 20.0 && ce[2] == 100.0 && ce[6] == 200.0);
+  auto sm = Linear::builder<double>().elements({0.0, 1.0}).knots({0.0, 1.0}).easing(ENTERP_EASE_SMOOTHSTEP).build().sample({0.5});
+  EXPECT(sm[0] == 0.5);
   // shards of one take agree with the whole
   auto whole = spline.take(1000).collect();
   auto part = spline.take(1000).shard(1, 3).collect();
