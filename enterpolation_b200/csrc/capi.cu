@@ -40,9 +40,9 @@ static const bool g_disable_rows = [] {
   return v && v[0] == '1';
 }();
 
-// Ablation switch (env ENTERP_COOP_SEARCH=1): warp-cooperative ballot search instead of per-thread.
-static const bool g_coop_search = [] {
-  const char* v = std::getenv("ENTERP_COOP_SEARCH");
+// Ablation switch (env ENTERP_NO_RECORDS=1): gather knots and elements separately in the Linear kernel.
+static const bool g_no_records = [] {
+  const char* v = std::getenv("ENTERP_NO_RECORDS");
   return v && v[0] == '1';
 }();
 
@@ -99,8 +99,10 @@ struct Replica {
   void* store = nullptr;
   void* elems = nullptr;
   void* rows = nullptr;
+  void* records = nullptr;
   void* pyramid = nullptr;              // all pivot levels, top first, one allocation
   uint32_t lvl_off[MAX_LEVELS] = {};    // element offsets of the levels inside it
+  uint32_t lvl_last[MAX_LEVELS] = {};   // last node index of each level
   int n_lvl = 0;
   uint32_t top_bytes = 0;               // size of levels [0, n_lvl-1) when they are worth staging in smem
   int n_top = 0;
@@ -132,6 +134,7 @@ struct CurveCore {
       cudaFree(rp->store);
       cudaFree(rp->elems);
       cudaFree(rp->rows);
+      cudaFree(rp->records);
       cudaFree(rp->pyramid);
       cudaFree(rp->invalid);
       delete rp;
@@ -178,12 +181,14 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   cudaError_t e = put(c->core->r.store, &rp->store);
   if (e == cudaSuccess) e = put(c->core->r.elems, &rp->elems);
   if (e == cudaSuccess && c->core->r.rows_mode) e = put(c->core->r.rows, &rp->rows);
+  if (e == cudaSuccess && c->core->r.rec_stride && !g_no_records) e = put(c->core->r.records, &rp->records);
   rp->n_lvl = (int)c->core->r.levels.level.size();
   if (rp->n_lvl > 0 && e == cudaSuccess) {
     std::vector<unsigned char> all;
     const size_t rs = rsize(c->core->r);
     for (int l = 0; l < rp->n_lvl; ++l) {
       rp->lvl_off[l] = (uint32_t)(all.size() / rs);
+      rp->lvl_last[l] = (uint32_t)(c->core->r.levels.level[l].size() / 32) - 1;  // nodes are 32-byte sectors
       all.insert(all.end(), c->core->r.levels.level[l].begin(), c->core->r.levels.level[l].end());
     }
     e = put(all, &rp->pyramid);
@@ -201,6 +206,7 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
     cudaFree(rp->store);
     cudaFree(rp->elems);
     cudaFree(rp->rows);
+    cudaFree(rp->records);
     cudaFree(rp->pyramid);
     cudaFree(rp->invalid);
     delete rp;
@@ -224,9 +230,12 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   d.vk = store ? store + r.vk_off : nullptr;
   d.ik = store ? store + r.ik_off : nullptr;
   d.elems = static_cast<const R*>(rp.elems);
+  d.records = static_cast<const R*>(rp.records);
+  d.rec_stride = r.rec_stride;
   d.n_lvl = rp.n_lvl;
   for (int l = 0; l < MAX_LEVELS; ++l) {
     d.lvl_off[l] = rp.lvl_off[l];
+    d.lvl_last[l] = rp.lvl_last[l];
     d.lvl[l] = l < rp.n_lvl ? static_cast<const R*>(rp.pyramid) + rp.lvl_off[l] : nullptr;
   }
   d.n_top = rp.n_top;
@@ -255,7 +264,6 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   d.easing_n = r.easing_n;
   d.ease_min = (R)r.ease_min;
   d.ease_max = (R)r.ease_max;
-  d.coop_search = g_coop_search ? 1 : 0;
   d.invalid = rp.invalid;
   return d;
 }

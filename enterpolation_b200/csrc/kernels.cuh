@@ -11,7 +11,7 @@
 
 namespace enterp {
 
-constexpr int MAX_LEVELS = 7;     // 32^7 > 2^31 searched knots
+constexpr int MAX_LEVELS = 16;    // pivot-tree depth: fan-out 8 (f32) / 4 (f64), 4^16 > 2^31 searched knots
 constexpr int MAX_DYN_DEGREE = 63;  // runtime-degree de Boor keeps its workspace in local memory
 constexpr int MAX_DYN_BEZIER = 256;
 constexpr int MAX_PRE = 4;   // nested input adaptors carried to the device
@@ -24,11 +24,14 @@ struct CurveDev {
   const R* vk;     // virtual knot vector (BorderBuffer / BorderDeletion already applied)
   const R* ik;     // innermost knot chain (what the search runs on)
   const R* elems;  // [n_elem][DH], homogeneous-lifted when weighted
+  const R* records;     // Linear over sorted knots: interval records (resolve.hpp), or nullptr
+  uint32_t rec_stride;  // in units of R
   const R* lvl[MAX_LEVELS];  // 32-ary pivot pyramid, top level first, NaN padded (one contiguous buffer)
   uint32_t lvl_off[MAX_LEVELS];  // offset of each level inside that buffer, in elements
+  uint32_t lvl_last[MAX_LEVELS]; // index of the last node of each level
   int n_lvl;
   int n_top;           // levels [0, n_top) are staged into shared memory by the kernel (0: none)
-  uint32_t top_bytes;  // their total size (multiple of 128)
+  uint32_t top_bytes;  // their total size (multiple of 32)
   uint32_t n_elem, inner_len, virt_len, degree;
   uint32_t imin, imax, map0, mapL;
   int32_t map_add;
@@ -42,7 +45,6 @@ struct CurveDev {
   // Linear easing of the lerp factor (easing/mod.rs, plateau.rs)
   int easing, easing_n;
   R ease_min, ease_max;
-  int coop_search;              // ablation switch: warp-cooperative instead of per-thread pivot search
   unsigned long long* invalid;  // device counter: samples where the reference would panic
 };
 
@@ -201,70 +203,72 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gmem_src, 
 // (list.rs:69-86) returns imin + this count on sorted knots, including ties (x == knot goes up),
 // repeated knots and NaN (-> 0).
 //
-// The search walks the 32-ary pivot pyramid top-down. Two evaluation strategies exist:
-//  * per-thread (default): every thread descends on its own, a 6-probe branch-free bisection inside
-//    each 32-entry block (one 128-byte line per level, so the top levels live in L1 and only the
-//    sectors actually probed travel from L2);
-//  * warp-cooperative (ENTERP_COOP_SEARCH=1, kept for the ablation in profiles/): the warp serves its
-//    32 samples one after the other, lane l compares pivot l, ballot + popc picks the child. It
-//    fetches whole lines but spends a full warp instruction per level PER SAMPLE; measured on B200
-//    it is issue-bound at ~1/8 of the per-thread throughput.
+// Layout: a pivot tree whose nodes are single 32-byte sectors (FAN = 8 f32 / 4 f64 keys, NaN padded;
+// NaN <= x is false, so padding never counts); level l+1 holds the last key of every node of level l.
+// A thread descends on its own, fetching ONE sector per level with a 256-bit load (LDG.E.256) and
+// counting the keys <= x in registers. Measured history on B200, C2 (2^20 knots, 2^28 samples):
+//   warp-cooperative 32-ary ballot search      9.5 G samples/s (a warp instruction per level PER SAMPLE)
+//   per-thread 6-probe bisection, 32-ary       21.5 G samples/s (25.7 L1 sector lookups, 8.0 L2 sectors per sample)
+//   + upper levels TMA-staged in shared memory 20.3 G samples/s (upper levels were L1 hits anyway)
+//   sector tree (this code)                    see profiles/README.md
 template <class R>
-__device__ __forceinline__ uint32_t coop_count_le(const CurveDev<R>& c, R x) {
-  const unsigned lane = threadIdx.x & 31u;
-  uint32_t mine = 0;
-#pragma unroll 4
-  for (int s = 0; s < 32; ++s) {
-    const R xs = __shfl_sync(0xffffffffu, x, s);
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int l = 0; l < MAX_LEVELS; ++l) {
-      if (l < c.n_lvl) {
-        const R v = __ldg(c.lvl[l] + ((size_t)cnt * 32u + lane));
-        cnt = cnt * 32u + __popc(__ballot_sync(0xffffffffu, v <= xs));
-      }
+struct Node;
+template <>
+struct Node<float> {
+  static constexpr int FAN = 8;
+  template <bool SMEM>
+  static __device__ __forceinline__ uint32_t count_le(const float* __restrict__ p, float x) {
+    float v[8];
+    if (SMEM) {
+      const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+      asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+          : "l"(p));
     }
-    if (lane == (unsigned)s) mine = cnt;
-  }
-  return mine;
-}
-
-// 6-probe branch-free bisection inside one 32-entry block: entries <= x form a prefix (sorted values,
-// then NaN padding: NaN <= x is false).
-template <class R, bool SMEM>
-__device__ __forceinline__ uint32_t block_count_le(const R* __restrict__ blk, R x) {
-  uint32_t pos = 0;
+    uint32_t c = 0;
 #pragma unroll
-  for (int step = 16; step >= 1; step >>= 1) {
-    const R v = SMEM ? blk[pos + step - 1] : __ldg(blk + pos + step - 1);
-    pos += (v <= x) ? step : 0;
+    for (int i = 0; i < 8; ++i) c += (v[i] <= x) ? 1u : 0u;
+    return c;
   }
-  const R last = SMEM ? blk[pos] : __ldg(blk + pos);
-  pos += (last <= x) ? 1u : 0u;  // 31 -> 32 (only possible in the top level)
-  return pos;
-}
+};
+template <>
+struct Node<double> {
+  static constexpr int FAN = 4;
+  template <bool SMEM>
+  static __device__ __forceinline__ uint32_t count_le(const double* __restrict__ p, double x) {
+    double v[4];
+    if (SMEM) {
+      const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+      asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    }
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c += (v[i] <= x) ? 1u : 0u;
+    return c;
+  }
+};
 
 // `top`: shared-memory copy of levels [0, n_top) (nullptr when nothing is staged).
 template <class R>
-__device__ __forceinline__ uint32_t thread_count_le(const CurveDev<R>& c, R x, const R* __restrict__ top) {
+__device__ __forceinline__ uint32_t count_le(const CurveDev<R>& c, R x, const R* __restrict__ top = nullptr) {
+  constexpr uint32_t FAN = Node<R>::FAN;
   uint32_t cnt = 0;
 #pragma unroll
   for (int l = 0; l < MAX_LEVELS; ++l) {
     if (l < c.n_lvl) {
+      // every key above was <= x: all nodes below are <= x too and the last one holds the remainder
+      cnt = min(cnt, c.lvl_last[l]);
       if (top != nullptr && l < c.n_top)
-        cnt = cnt * 32u + block_count_le<R, true>(top + c.lvl_off[l] + (size_t)cnt * 32u, x);
+        cnt = cnt * FAN + Node<R>::template count_le<true>(top + c.lvl_off[l] + (size_t)cnt * FAN, x);
       else
-        cnt = cnt * 32u + block_count_le<R, false>(c.lvl[l] + (size_t)cnt * 32u, x);
+        cnt = cnt * FAN + Node<R>::template count_le<false>(c.lvl[l] + (size_t)cnt * FAN, x);
     }
   }
   return cnt;
-}
-
-// All lanes of the warp must call (the cooperative variant shuffles).
-template <class R>
-__device__ __forceinline__ uint32_t count_le(const CurveDev<R>& c, R x, const R* __restrict__ top = nullptr) {
-  if (c.coop_search) return coop_count_le(c, x);
-  return thread_count_le(c, x, top);
 }
 
 // Stages the top pyramid levels into dynamic shared memory when the host asked for it; returns the
@@ -338,7 +342,15 @@ __device__ __forceinline__ bool linear_border(const CurveDev<R>& c, R x, uint32_
     const bool edge = (m == len) || (m == 0);
     imax = m == len ? len - 1 : (m == 0 ? 1u : m);
     imin = imax - 1;
-    const R kmin = __ldg(c.ik + imin), kmax = __ldg(c.ik + imax);
+    R kmin, kmax;
+    if (c.records) {
+      const R* __restrict__ rec = c.records + (size_t)imin * c.rec_stride;
+      kmin = __ldg(rec);
+      kmax = __ldg(rec + 1);
+    } else {
+      kmin = __ldg(c.ik + imin);
+      kmax = __ldg(c.ik + imax);
+    }
     const R div = xsub(kmax, kmin);
     // linear_factor (checked, 232-248) on the edges, linear_factor_unchecked (212-224) inside
     factor = (edge && div == R(0)) ? div : xdiv(xsub(x, kmin), div);
@@ -477,8 +489,9 @@ __global__ void __launch_bounds__(MAX_BLOCK) linear_kernel(const CurveDev<R> c, 
     if (c.easing) f = apply_easing(c, f);  // easing.eval(factor), linear/mod.rs:127
     const R omf = xsub(R(1), f);
     R w[DH];
-    const R* __restrict__ a = c.elems + (size_t)imin * DH;
-    const R* __restrict__ b = c.elems + (size_t)imax * DH;
+    // both elements sit behind the two knots in the interval record when there is one (imax == imin + 1)
+    const R* __restrict__ a = (!EQUI && c.records) ? c.records + (size_t)imin * c.rec_stride + 2 : c.elems + (size_t)imin * DH;
+    const R* __restrict__ b = (!EQUI && c.records) ? a + DH : c.elems + (size_t)imax * DH;
 #pragma unroll
     for (int k = 0; k < DH; ++k) w[k] = merge1(__ldg(a + k), __ldg(b + k), f, omf);
     finish_and_store<R, DH, PROJ>(out, i, w, valid, vec_ok, c.invalid);

@@ -432,19 +432,21 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
   }
   if (d.knot_base == ENTERP_KNOTS_EQUIDISTANT) r.eq_first = inner[r.imin < s.inner_len ? r.imin : s.inner_len - 1];
 
-  // 32-ary pivot pyramid for the sorted search
+  // Pivot tree for the sorted search: nodes are 32-byte sectors (FAN keys), bottom level = the searched
+  // knot range, each upper level = last key of every node below; all NaN padded (see kernels.cuh).
   if (d.knot_base == ENTERP_KNOTS_SORTED) {
+    const uint64_t FAN = 32 / sizeof(R);
     const uint64_t W = r.imax - r.imin;
     std::vector<std::vector<R>> lv;
-    std::vector<R> cur((W + 31) / 32 * 32, nan);
-    if (cur.empty()) cur.assign(32, nan);
+    std::vector<R> cur((W + FAN - 1) / FAN * FAN, nan);
+    if (cur.empty()) cur.assign(FAN, nan);
     for (uint64_t i = 0; i < W; ++i) cur[i] = inner[r.imin + i];
     lv.push_back(cur);
-    while (lv.back().size() > 32) {
+    while (lv.back().size() > FAN) {
       const std::vector<R>& below = lv.back();
-      const uint64_t blocks = below.size() / 32;
-      std::vector<R> up((blocks + 31) / 32 * 32, nan);
-      for (uint64_t b = 0; b < blocks; ++b) up[b] = below[32 * b + 31];  // NaN if the block is partial
+      const uint64_t nodes = below.size() / FAN;
+      std::vector<R> up((nodes + FAN - 1) / FAN * FAN, nan);
+      for (uint64_t b = 0; b < nodes; ++b) up[b] = below[FAN * b + FAN - 1];  // NaN if the node is partial
       lv.push_back(up);
     }
     for (size_t i = lv.size(); i-- > 0;) {
@@ -455,6 +457,26 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
   }
 
   if (d.kind == ENTERP_BSPLINE) build_rows<R>(d, s, r, vk);
+  if (d.kind == ENTERP_LINEAR && d.knot_base == ENTERP_KNOTS_SORTED && s.inner_len >= 2) {
+    const uint32_t per = 16 / sizeof(R);
+    const uint32_t stride = (uint32_t)((2 + 2 * r.dh + per - 1) / per * per);
+    if (stride * sizeof(R) <= 64) {
+      const R* el = reinterpret_cast<const R*>(r.elems.data());
+      std::vector<R> rec((size_t)(s.inner_len - 1) * stride, R(0));
+      for (uint64_t j = 0; j + 1 < s.inner_len; ++j) {
+        R* p = rec.data() + j * stride;
+        p[0] = inner[j];
+        p[1] = inner[j + 1];
+        for (int c = 0; c < r.dh; ++c) {
+          p[2 + c] = el[j * r.dh + c];
+          p[2 + r.dh + c] = el[(j + 1) * r.dh + c];
+        }
+      }
+      r.rec_stride = stride;
+      r.records.resize(rec.size() * sizeof(R));
+      std::memcpy(r.records.data(), rec.data(), r.records.size());
+    }
+  }
   if (d.kind == ENTERP_LINEAR) {
     r.easing = d.easing;
     r.easing_n = d.easing_n;

@@ -18,8 +18,8 @@ enum Adaptor : int32_t { AD_NONE = 0, AD_BORDER_BUFFER = 1, AD_BORDER_DELETION =
 enum Stage : int32_t { STAGE_ELEMENTS = 0, STAGE_KNOTS = 1, STAGE_SPACE = 2 };
 
 struct SearchLevels {
-  // 32-ary pivot pyramid over the searched inner knot range, top level first; every level is
-  // padded to a multiple of 32 entries with NaN (NaN <= x is false, so padding never counts).
+  // Pivot tree over the searched inner knot range, top level first; nodes are 32-byte sectors
+  // (8 f32 / 4 f64 keys) and every level is NaN padded (NaN <= x is false, so padding never counts).
   std::vector<std::vector<unsigned char>> level;  // raw R values
 };
 
@@ -51,6 +51,10 @@ struct Resolved {
   // Bezier TransformInput (base/adaptors.rs:137-139)
   int32_t has_transform = 0;
   double in_add = 0, in_mul = 1;
+  // Linear over sorted knots: one record per knot interval j = [k_j, k_{j+1}, e_j[0..dh), e_{j+1}[0..dh)],
+  // padded to a multiple of 16 bytes, so that the lerp's operands arrive in one or two 32-byte sectors
+  std::vector<unsigned char> records;
+  uint32_t rec_stride = 0;  // in units of R; 0 = no record table
   // Linear easing (easing/mod.rs:86-132, plateau.rs): kind, N of smoothstart/smoothend, Plateau min/max in R
   int32_t easing = 0, easing_n = 0;
   double ease_min = 0, ease_max = 1;

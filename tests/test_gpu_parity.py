@@ -308,3 +308,28 @@ def test_linear_easings(scalar, knots_kind):
             t = adversarial(np.linspace(-1.0, 1.0, 21), dtype, rng, n_random=1500)
         b = b.easing(ez)
         check_adapted(b.build(), oracle.OracleCurve(b.to_desc()), t, f"easing {ez} {knots_kind} {scalar}")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 9, 16, 17, 31, 32, 33, 63, 64, 65, 255, 256, 257, 1025, 4100])
+def test_pivot_tree_shapes(scalar, n):
+    """Every node-count corner of the pivot tree (full / partial last nodes, 1..5 levels), with x below,
+    at and beyond every knot — in particular x >= all knots, where every upper-level key is <= x."""
+    dtype = DT[scalar]
+    knots = sorted_knots(n, dtype, 0x71 + n)
+    el = rand_elements(n, 1, dtype, 0x72)
+    b = Linear.builder().elements(el).knots(knots)
+    t = np.concatenate([knots, np.nextafter(knots, dtype(np.inf)), np.nextafter(knots, dtype(-np.inf)),
+                        np.array([knots[0] - 1, knots[-1] + 1, knots[-1] * 4, np.inf, -np.inf, np.nan], dtype=dtype)]).astype(dtype)
+    curve, ref = b.build(), oracle.OracleCurve(b.to_desc())
+    tt = torch.from_numpy(t).cuda()
+    idx, fac = curve.span_device(tt)
+    widx, wfac = ref.span(t)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32), widx), f"linear span n={n}"
+    assert_bits_equal(curve.sample_device(tt).cpu().numpy(), ref.eval(t), f"linear eval n={n}")
+    if n >= 4:  # the same knots as an open quadratic B-spline (k knots, e = k - 1 elements)
+        b2 = BSpline.builder().elements(rand_elements(n - 1, 2, dtype, 0x73)).knots(knots).dynamic()
+        c2, r2 = b2.build(), oracle.OracleCurve(b2.to_desc())
+        idx, _ = c2.span_device(tt)
+        assert np.array_equal(idx.cpu().numpy().view(np.uint32), r2.span(t)[0]), f"bspline span n={n}"
+        assert_bits_equal(c2.sample_device(tt).cpu().numpy(), r2.eval(t), f"bspline eval n={n}")
