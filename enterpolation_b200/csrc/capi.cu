@@ -46,14 +46,12 @@ static const bool g_no_records = [] {
   return v && v[0] == '1';
 }();
 
-// Opt-in (env ENTERP_SMEM_PIVOTS=1): TMA-stage the pivot levels above the bottom one into shared memory.
-// Off by default: measured on B200 (C2, 2^20 knots, 2^28 samples) it does not pay — the upper levels
-// already live in L1, the kernel is bound by the L2 sector traffic of the bottom level and the element
-// gather, and one fat CTA per SM halves the warps in flight (20.3 vs 21.5 G samples/s).
-static const bool g_smem_pivots = [] {
-  const char* v = std::getenv("ENTERP_SMEM_PIVOTS");
+// Ablation switch (env ENTERP_NO_SMEM_PIVOTS=1): leave every pivot level in global memory / L1.
+static const bool g_no_smem_pivots = [] {
+  const char* v = std::getenv("ENTERP_NO_SMEM_PIVOTS");
   return v && v[0] == '1';
 }();
+constexpr size_t SEARCH_SMEM_BUDGET = 96u * 1024u;
 
 static thread_local std::string t_cuda_error;
 static enterp_status cuda_fail(cudaError_t e, const char* where) {
@@ -194,10 +192,15 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
     e = put(all, &rp->pyramid);
     // Stage everything above the bottom level in shared memory when that is big enough to fall out of
     // L1 (small pyramids stay L1-resident anyway) and small enough to fit.
-    const size_t top = (size_t)rp->lvl_off[rp->n_lvl - 1] * rs;
-    if (rp->n_lvl >= 2 && top >= 8u * 1024u && top <= SEARCH_SMEM_MAX && g_smem_pivots) {
+    // Stage as many top levels as fit the per-CTA budget in shared memory (two fat CTAs per SM). Small
+    // trees stay in L1 on their own; only trees whose upper levels exceed ~8 KB are worth staging.
+    int n_top = 0;
+    for (int l = 0; l + 1 < rp->n_lvl; ++l)
+      if ((size_t)rp->lvl_off[l + 1] * rs <= SEARCH_SMEM_BUDGET) n_top = l + 1;
+    const size_t top = n_top ? (size_t)rp->lvl_off[n_top] * rs : 0;
+    if (top >= 8u * 1024u && !g_no_smem_pivots) {
       rp->top_bytes = (uint32_t)top;
-      rp->n_top = rp->n_lvl - 1;
+      rp->n_top = n_top;
     }
   }
   if (e == cudaSuccess) e = cudaMalloc((void**)&rp->invalid, sizeof(unsigned long long));

@@ -342,15 +342,7 @@ __device__ __forceinline__ bool linear_border(const CurveDev<R>& c, R x, uint32_
     const bool edge = (m == len) || (m == 0);
     imax = m == len ? len - 1 : (m == 0 ? 1u : m);
     imin = imax - 1;
-    R kmin, kmax;
-    if (c.records) {
-      const R* __restrict__ rec = c.records + (size_t)imin * c.rec_stride;
-      kmin = __ldg(rec);
-      kmax = __ldg(rec + 1);
-    } else {
-      kmin = __ldg(c.ik + imin);
-      kmax = __ldg(c.ik + imax);
-    }
+    const R kmin = __ldg(c.ik + imin), kmax = __ldg(c.ik + imax);
     const R div = xsub(kmax, kmin);
     // linear_factor (checked, 232-248) on the edges, linear_factor_unchecked (212-224) inside
     factor = (edge && div == R(0)) ? div : xdiv(xsub(x, kmin), div);
@@ -468,6 +460,46 @@ __global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(
   }
 }
 
+// Vector loads of `N` values from a 16-byte aligned address (N * sizeof(R) a multiple of 16). When every
+// record is a multiple of 32 bytes (so each one is 32-byte aligned) 256-bit loads (LDG.E.256) are used.
+template <int N>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[N]) {
+  static_assert(N % 4 == 0, "16-byte multiples");
+  if constexpr (N % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 8)
+      asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          : "=f"(v[i]), "=f"(v[i + 1]), "=f"(v[i + 2]), "=f"(v[i + 3]), "=f"(v[i + 4]), "=f"(v[i + 5]), "=f"(v[i + 6]), "=f"(v[i + 7])
+          : "l"(p + i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+      v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void load_vec(const double* __restrict__ p, double (&v)[N]) {
+  static_assert(N % 2 == 0, "16-byte multiples");
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4)
+      asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[i]), "=d"(v[i + 1]), "=d"(v[i + 2]), "=d"(v[i + 3]) : "l"(p + i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      const double2 t = __ldg(reinterpret_cast<const double2*>(p + i));
+      v[i] = t.x; v[i + 1] = t.y;
+    }
+  }
+}
+// record stride (in R) of the Linear interval table for DH components — must match resolve.cpp
+template <class R>
+__host__ __device__ constexpr int linear_rec_stride(int DH) {
+  return (2 + 2 * DH + (16 / (int)sizeof(R)) - 1) / (16 / (int)sizeof(R)) * (16 / (int)sizeof(R));
+}
+
 // =================================================================================================
 // Linear: upper_border -> two element fetches -> merge (linear/mod.rs:122-128), Identity easing.
 // =================================================================================================
@@ -484,16 +516,36 @@ __global__ void __launch_bounds__(MAX_BLOCK) linear_kernel(const CurveDev<R> c, 
     R x = active ? apply_pre(c, sample_param(s, i)) : R(0);
     uint32_t imin, imax;
     R f;
-    const bool valid = linear_border<R, EQUI>(c, x, imin, imax, f, top);
-    if (!active) continue;
-    if (c.easing) f = apply_easing(c, f);  // easing.eval(factor), linear/mod.rs:127
-    const R omf = xsub(R(1), f);
     R w[DH];
-    // both elements sit behind the two knots in the interval record when there is one (imax == imin + 1)
-    const R* __restrict__ a = (!EQUI && c.records) ? c.records + (size_t)imin * c.rec_stride + 2 : c.elems + (size_t)imin * DH;
-    const R* __restrict__ b = (!EQUI && c.records) ? a + DH : c.elems + (size_t)imax * DH;
+    bool valid = true;
+    if (!EQUI && c.records != nullptr) {
+      // sorted knots with an interval-record table: search, then ONE vector load brings both knots and
+      // both elements of the interval (list.rs:169-203 upper_border; linear/mod.rs:122-128)
+      constexpr int STRIDE = linear_rec_stride<R>(DH);
+      const uint32_t len = c.inner_len;
+      const uint32_t m = count_le(c, x, top);
+      const bool edge = (m == len) || (m == 0);
+      imax = m == len ? len - 1 : (m == 0 ? 1u : m);
+      imin = imax - 1;
+      if (!active) continue;
+      R rec[STRIDE];
+      load_vec<STRIDE>(c.records + (size_t)imin * STRIDE, rec);
+      const R div = xsub(rec[1], rec[0]);
+      f = (edge && div == R(0)) ? div : xdiv(xsub(x, rec[0]), div);
+      if (c.easing) f = apply_easing(c, f);
+      const R omf = xsub(R(1), f);
 #pragma unroll
-    for (int k = 0; k < DH; ++k) w[k] = merge1(__ldg(a + k), __ldg(b + k), f, omf);
+      for (int k = 0; k < DH; ++k) w[k] = merge1(rec[2 + k], rec[2 + DH + k], f, omf);
+    } else {
+      valid = linear_border<R, EQUI>(c, x, imin, imax, f, top);
+      if (!active) continue;
+      if (c.easing) f = apply_easing(c, f);  // easing.eval(factor), linear/mod.rs:127
+      const R omf = xsub(R(1), f);
+      const R* __restrict__ a = c.elems + (size_t)imin * DH;
+      const R* __restrict__ b = c.elems + (size_t)imax * DH;
+#pragma unroll
+      for (int k = 0; k < DH; ++k) w[k] = merge1(__ldg(a + k), __ldg(b + k), f, omf);
+    }
     finish_and_store<R, DH, PROJ>(out, i, w, valid, vec_ok, c.invalid);
   }
 }
