@@ -98,6 +98,7 @@ struct Replica {
   void* elems = nullptr;
   void* rows = nullptr;
   void* records = nullptr;
+  void* knot_rows = nullptr;
   void* pyramid = nullptr;              // all pivot levels, top first, one allocation
   uint32_t lvl_off[MAX_LEVELS] = {};    // element offsets of the levels inside it
   uint32_t lvl_last[MAX_LEVELS] = {};   // last node index of each level
@@ -133,6 +134,7 @@ struct CurveCore {
       cudaFree(rp->elems);
       cudaFree(rp->rows);
       cudaFree(rp->records);
+      cudaFree(rp->knot_rows);
       cudaFree(rp->pyramid);
       cudaFree(rp->invalid);
       delete rp;
@@ -180,6 +182,7 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   if (e == cudaSuccess) e = put(c->core->r.elems, &rp->elems);
   if (e == cudaSuccess && c->core->r.rows_mode) e = put(c->core->r.rows, &rp->rows);
   if (e == cudaSuccess && c->core->r.rec_stride && !g_no_records) e = put(c->core->r.records, &rp->records);
+  if (e == cudaSuccess && c->core->r.krow_stride && !g_no_records) e = put(c->core->r.knot_rows, &rp->knot_rows);
   rp->n_lvl = (int)c->core->r.levels.level.size();
   if (rp->n_lvl > 0 && e == cudaSuccess) {
     std::vector<unsigned char> all;
@@ -210,6 +213,7 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
     cudaFree(rp->elems);
     cudaFree(rp->rows);
     cudaFree(rp->records);
+    cudaFree(rp->knot_rows);
     cudaFree(rp->pyramid);
     cudaFree(rp->invalid);
     delete rp;
@@ -233,6 +237,8 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   d.vk = store ? store + r.vk_off : nullptr;
   d.ik = store ? store + r.ik_off : nullptr;
   d.elems = static_cast<const R*>(rp.elems);
+  d.knot_rows = static_cast<const R*>(rp.knot_rows);
+  d.krow_lo = (uint32_t)r.degree;
   d.records = static_cast<const R*>(rp.records);
   d.rec_stride = r.rec_stride;
   d.n_lvl = rp.n_lvl;

@@ -24,6 +24,8 @@ struct CurveDev {
   const R* vk;     // virtual knot vector (BorderBuffer / BorderDeletion already applied)
   const R* ik;     // innermost knot chain (what the search runs on)
   const R* elems;  // [n_elem][DH], homogeneous-lifted when weighted
+  const R* knot_rows;   // B-spline, degree 1..7: padded per-span knot rows (resolve.hpp), or nullptr
+  uint32_t krow_lo;     // span index of knot row 0
   const R* records;     // Linear over sorted knots: interval records (resolve.hpp), or nullptr
   uint32_t rec_stride;  // in units of R
   const R* lvl[MAX_LEVELS];  // 32-ary pivot pyramid, top level first, NaN padded (one contiguous buffer)
@@ -393,6 +395,40 @@ __device__ __forceinline__ void finish_and_store(R* __restrict__ out, unsigned l
   store_elem<R, D>(out, i, v, vec_ok);
 }
 
+// Vector loads of `N` values from a 16-byte aligned address (N * sizeof(R) a multiple of 16); 256-bit
+// loads (LDG.E.256) when the caller guarantees 32-byte alignment (ALIGN32).
+template <int N, bool ALIGN32>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[N]) {
+  static_assert(N % 4 == 0, "16-byte multiples");
+  if constexpr (ALIGN32 && N % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 8)
+      asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          : "=f"(v[i]), "=f"(v[i + 1]), "=f"(v[i + 2]), "=f"(v[i + 3]), "=f"(v[i + 4]), "=f"(v[i + 5]), "=f"(v[i + 6]), "=f"(v[i + 7])
+          : "l"(p + i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+      v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+  }
+}
+template <int N, bool ALIGN32>
+__device__ __forceinline__ void load_vec(const double* __restrict__ p, double (&v)[N]) {
+  static_assert(N % 2 == 0, "16-byte multiples");
+  if constexpr (ALIGN32 && N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4)
+      asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[i]), "=d"(v[i + 1]), "=d"(v[i + 2]), "=d"(v[i + 3]) : "l"(p + i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      const double2 t = __ldg(reinterpret_cast<const double2*>(p + i));
+      v[i] = t.x; v[i + 1] = t.y;
+    }
+  }
+}
 // Largest block the generic B-spline kernel may be launched with: 1024 threads (one fat CTA per SM, used
 // when big pivot tables are staged in shared memory) only where the register working set fits the
 // 64-register cap that implies; otherwise 256.
@@ -427,10 +463,26 @@ __global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(
     const R* __restrict__ vk = c.vk + first;
     const R* __restrict__ el = c.elems + (size_t)first * DH;
     if (DEG > 0) {
+      // gathers: vector loads (LDG.E.256 / .128) where the layout guarantees alignment
+      constexpr int KSTR = (2 * P_CAP + (32 / (int)sizeof(R)) - 1) / (32 / (int)sizeof(R)) * (32 / (int)sizeof(R));
+      if (c.knot_rows != nullptr) {
+        R kr[KSTR];
+        load_vec<KSTR, true>(c.knot_rows + (size_t)(index - c.krow_lo) * KSTR, kr);
 #pragma unroll
-      for (int m = 0; m < 2 * P_CAP; ++m) kn[m] = __ldg(vk + m);
+        for (int m = 0; m < 2 * P_CAP; ++m) kn[m] = kr[m];
+      } else {
 #pragma unroll
-      for (int m = 0; m < (P_CAP + 1) * DH; ++m) ws[m] = __ldg(el + m);
+        for (int m = 0; m < 2 * P_CAP; ++m) kn[m] = __ldg(vk + m);
+      }
+      if constexpr ((DH * (int)sizeof(R)) % 16 == 0) {
+        R ev[(P_CAP + 1) * DH];
+        load_vec<(P_CAP + 1) * DH, (DH * (int)sizeof(R)) % 32 == 0>(el, ev);  // el is DH*sizeof(R)-aligned
+#pragma unroll
+        for (int m = 0; m < (P_CAP + 1) * DH; ++m) ws[m] = ev[m];
+      } else {
+#pragma unroll
+        for (int m = 0; m < (P_CAP + 1) * DH; ++m) ws[m] = __ldg(el + m);
+      }
 #pragma unroll
       for (int r = 1; r <= P_CAP; ++r) {
 #pragma unroll
@@ -460,40 +512,6 @@ __global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(
   }
 }
 
-// Vector loads of `N` values from a 16-byte aligned address (N * sizeof(R) a multiple of 16). When every
-// record is a multiple of 32 bytes (so each one is 32-byte aligned) 256-bit loads (LDG.E.256) are used.
-template <int N>
-__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[N]) {
-  static_assert(N % 4 == 0, "16-byte multiples");
-  if constexpr (N % 8 == 0) {
-#pragma unroll
-    for (int i = 0; i < N; i += 8)
-      asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-          : "=f"(v[i]), "=f"(v[i + 1]), "=f"(v[i + 2]), "=f"(v[i + 3]), "=f"(v[i + 4]), "=f"(v[i + 5]), "=f"(v[i + 6]), "=f"(v[i + 7])
-          : "l"(p + i));
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; i += 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
-      v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
-    }
-  }
-}
-template <int N>
-__device__ __forceinline__ void load_vec(const double* __restrict__ p, double (&v)[N]) {
-  static_assert(N % 2 == 0, "16-byte multiples");
-  if constexpr (N % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < N; i += 4)
-      asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[i]), "=d"(v[i + 1]), "=d"(v[i + 2]), "=d"(v[i + 3]) : "l"(p + i));
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; i += 2) {
-      const double2 t = __ldg(reinterpret_cast<const double2*>(p + i));
-      v[i] = t.x; v[i + 1] = t.y;
-    }
-  }
-}
 // record stride (in R) of the Linear interval table for DH components — must match resolve.cpp
 template <class R>
 __host__ __device__ constexpr int linear_rec_stride(int DH) {
@@ -529,7 +547,7 @@ __global__ void __launch_bounds__(MAX_BLOCK) linear_kernel(const CurveDev<R> c, 
       imin = imax - 1;
       if (!active) continue;
       R rec[STRIDE];
-      load_vec<STRIDE>(c.records + (size_t)imin * STRIDE, rec);
+      load_vec<STRIDE, (STRIDE * (int)sizeof(R)) % 32 == 0>(c.records + (size_t)imin * STRIDE, rec);
       const R div = xsub(rec[1], rec[0]);
       f = (edge && div == R(0)) ? div : xdiv(xsub(x, rec[0]), div);
       if (c.easing) f = apply_easing(c, f);

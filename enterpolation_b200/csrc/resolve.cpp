@@ -457,6 +457,19 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
   }
 
   if (d.kind == ENTERP_BSPLINE) build_rows<R>(d, s, r, vk);
+  if (d.kind == ENTERP_BSPLINE && s.degree >= 1 && s.degree <= 7) {
+    const uint32_t per = 32 / sizeof(R);
+    const uint32_t stride = (uint32_t)((2 * s.degree + per - 1) / per * per);
+    const uint64_t lo = s.degree, hi = s.virt_len - s.degree;
+    if ((hi - lo + 1) * stride * sizeof(R) <= (1ull << 28)) {
+      std::vector<R> kr((size_t)(hi - lo + 1) * stride, R(0));
+      for (uint64_t idx = lo; idx <= hi; ++idx)
+        for (uint64_t m = 0; m < 2 * s.degree; ++m) kr[(idx - lo) * stride + m] = vk[idx - s.degree + m];
+      r.krow_stride = stride;
+      r.knot_rows.resize(kr.size() * sizeof(R));
+      std::memcpy(r.knot_rows.data(), kr.data(), r.knot_rows.size());
+    }
+  }
   if (d.kind == ENTERP_LINEAR && d.knot_base == ENTERP_KNOTS_SORTED && s.inner_len >= 2) {
     const uint32_t per = 16 / sizeof(R);
     const uint32_t stride = (uint32_t)((2 + 2 * r.dh + per - 1) / per * per);

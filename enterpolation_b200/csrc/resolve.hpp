@@ -51,6 +51,10 @@ struct Resolved {
   // Bezier TransformInput (base/adaptors.rs:137-139)
   int32_t has_transform = 0;
   double in_add = 0, in_mul = 1;
+  // Generic B-spline kernel, degree 1..7: the 2*degree knots of every span index in [lo, hi], padded to
+  // 32 bytes, so that they arrive with one or two 256-bit loads instead of 2*degree scalar ones
+  std::vector<unsigned char> knot_rows;
+  uint32_t krow_stride = 0;  // in units of R; 0 = no table
   // Linear over sorted knots: one record per knot interval j = [k_j, k_{j+1}, e_j[0..dh), e_{j+1}[0..dh)],
   // padded to a multiple of 16 bytes, so that the lerp's operands arrive in one or two 32-byte sectors
   std::vector<unsigned char> records;
