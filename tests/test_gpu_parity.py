@@ -333,3 +333,104 @@ def test_pivot_tree_shapes(scalar, n):
         idx, _ = c2.span_device(tt)
         assert np.array_equal(idx.cpu().numpy().view(np.uint32), r2.span(t)[0]), f"bspline span n={n}"
         assert_bits_equal(c2.sample_device(tt).cpu().numpy(), r2.eval(t), f"bspline eval n={n}")
+
+
+# ---- edge cases: empty / ragged / misaligned / huge index ranges / concurrency --------------------------
+def _c5_like(scalar="f32", stops=7, dim=4):
+    dtype = DT[scalar]
+    el = rand_elements(stops, dim, dtype, 0x81)
+    return BSpline.builder().clamped().elements(el).equidistant(scalar).degree(3).normalized().dynamic()
+
+
+def test_empty_and_single_sample():
+    b = _c5_like()
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    assert c.sample(np.zeros(0, np.float32)).shape == (0, 4)
+    assert c.take_device(10, 3, 0).shape == (0, 4)
+    assert_bits_equal(np.asarray(c.sample(np.array([0.3], np.float32))), r.eval(np.array([0.3], np.float32)))
+    # take(1): step = (end-start)/fl(0) -> the single parameter is NaN; the reference panics on it
+    before = c.invalid_count()
+    got = c.take_device(1).cpu().numpy()
+    assert np.all(np.isnan(got)) and c.invalid_count() == before + 1
+    assert np.all(np.isnan(r.take(1)))
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1023, 100003])
+@pytest.mark.parametrize("scalar,dim", [("f32", 4), ("f32", 3), ("f64", 1), ("f64", 2)])
+def test_ragged_sizes_and_offsets(n, scalar, dim):
+    """Tile tails of the 2-samples-per-trip kernel, for take (with a global offset) and batch."""
+    b = _c5_like(scalar, 9, dim)
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    assert_bits_equal(c.take_device(n).cpu().numpy(), r.take(n), f"take {n}")
+    total = n + 12345
+    assert_bits_equal(c.take_device(total, 777, n).cpu().numpy(), r.take(total, 777, n), f"take window {n}")
+    t = (u01(n, 0x82, DT[scalar]) * DT[scalar](1.5) - DT[scalar](0.25)).astype(DT[scalar])
+    assert_bits_equal(c.sample_device(torch.from_numpy(t).cuda()).cpu().numpy(), r.eval(t), f"batch {n}")
+
+
+def test_misaligned_output_pointer_uses_scalar_stores():
+    b = _c5_like("f32", 6, 4)
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    n = 1000
+    buf = torch.empty(n * 4 + 1, dtype=torch.float32, device="cuda")
+    out = buf[1:].view(n, 4)  # 4-byte aligned only
+    assert out.data_ptr() % 16 != 0
+    c.take_device(n, out=out)
+    assert_bits_equal(out.cpu().numpy(), r.take(n), "misaligned take")
+    t = u01(n, 0x83, np.float32)
+    c.sample_device(torch.from_numpy(t).cuda(), out=out)
+    assert_bits_equal(out.cpu().numpy(), r.eval(t), "misaligned batch")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+def test_huge_global_index_range(scalar):
+    """take(2^40): 64-bit global indices and fl(i) beyond 2^32 (shards of a very long stepper)."""
+    b = _c5_like(scalar, 8, 2)
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    n_total = 1 << 40
+    for first in (0, (1 << 32) - 1000, (1 << 39) + 12345, n_total - 5000):
+        assert_bits_equal(c.take_device(n_total, first, 5000).cpu().numpy(), r.take(n_total, first, 5000), f"{scalar} first={first}")
+
+
+def test_concurrent_host_threads_share_a_curve():
+    """`eval(&self)` re-entrancy (space.rs:63-66): several host threads drive one handle on their own streams."""
+    import threading
+    b = _c5_like("f32", 11, 4)
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    c.upload(0)
+    want = {k: r.take(5000 + k, k, 4000) for k in range(4)}
+    got, errs = {}, []
+
+    def work(k):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(20):
+                    o = c.take_device(5000 + k, k, 4000, stream=s)
+                s.synchronize()
+                got[k] = o.cpu().numpy()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for k in range(4):
+        assert_bits_equal(got[k], want[k], f"thread {k}")
+
+
+def test_degree_limits_and_unsupported():
+    from enterpolation_b200 import Unsupported
+    # runtime-degree path: degree 20 (DynSpace semantics), and the documented limit (degree > 63)
+    for deg in (8, 20, 63):
+        e = deg + 5
+        knots = sorted_knots(e + deg - 1, np.float64, 0x90 + deg)
+        b = BSpline.builder().elements(rand_elements(e, 2, np.float64, 0x91)).knots(knots).dynamic()
+        c, r = b.build(), oracle.OracleCurve(b.to_desc())
+        t = np.linspace(float(r.domain()[0]) - 0.1, float(r.domain()[1]) + 0.1, 301)
+        assert_bits_equal(np.asarray(c.sample(t)), r.eval(t), f"degree {deg}")
+    e = 70
+    b = BSpline.builder().elements(np.zeros(e)).knots(np.arange(e + 63, dtype=np.float64)).dynamic()  # degree 64
+    with pytest.raises(Unsupported):
+        b.build().sample(np.array([1.0]))
