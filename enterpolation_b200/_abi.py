@@ -73,7 +73,7 @@ class CurveInfo(C.Structure):
 EXPORTS = [
     "enterp_curve_validate", "enterp_curve_create", "enterp_curve_destroy", "enterp_curve_get_info", "enterp_curve_domain",
     "enterp_curve_clamp", "enterp_curve_slice", "enterp_curve_upload", "enterp_eval_batch", "enterp_eval_take", "enterp_span_batch",
-    "enterp_span_take", "enterp_stepper", "enterp_bezier_many_take", "enterp_sample_host",
+    "enterp_span_take", "enterp_stepper", "enterp_bezier_many_take", "enterp_bezier_tangent_batch", "enterp_bezier_derivatives_batch", "enterp_sample_host",
     "enterp_take_host", "enterp_host_alloc", "enterp_host_free", "enterp_invalid_count",
     "enterp_status_str", "enterp_last_cuda_error", "enterp_device_count", "enterp_launch_count",
     "enterp_version",
@@ -127,6 +127,10 @@ def load_library() -> C.CDLL:
     lib.enterp_stepper.restype = i32
     lib.enterp_bezier_many_take.argtypes = [i32, i32, u64, C.c_uint32, vp, C.c_uint32, i32, vp, vp]
     lib.enterp_bezier_many_take.restype = i32
+    lib.enterp_bezier_tangent_batch.argtypes = [vp, i32, vp, u64, vp, vp]
+    lib.enterp_bezier_tangent_batch.restype = i32
+    lib.enterp_bezier_derivatives_batch.argtypes = [vp, i32, vp, u64, C.c_uint32, vp, vp]
+    lib.enterp_bezier_derivatives_batch.restype = i32
     lib.enterp_sample_host.argtypes = [vp, i32, vp, u64, vp]
     lib.enterp_sample_host.restype = i32
     lib.enterp_take_host.argtypes = [vp, i32, u64, u64, u64, vp]

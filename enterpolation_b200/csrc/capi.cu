@@ -674,6 +674,43 @@ ENTERP_API enterp_status enterp_bezier_many_take(int scalar, int dim, uint64_t n
   return ENTERP_OK;
 }
 
+static enterp_status bezier_deriv_common(enterp_curve* c, int device, const void* t_dev, uint64_t n, uint32_t k,
+                                         int tangent, void* out_dev, void* stream) {
+  if (!c) return ENTERP_INVALID_ARGUMENT;
+  const Resolved& r = c->core->r;
+  if (r.kind != ENTERP_BEZIER || r.weighted || !c->pre.empty()) return ENTERP_UNSUPPORTED;
+  if (n == 0) return ENTERP_OK;
+  if (!t_dev || !out_dev) return ENTERP_INVALID_ARGUMENT;
+  if (r.n_elem > (uint64_t)MAX_DERIV_N || k > (uint32_t)MAX_DERIV_N) return ENTERP_UNSUPPORTED;
+  if (k == 0) return ENTERP_OK;  // `[T; 0]`: nothing to write
+  // gen_with_deriatives::<K> slices `grad[..=min(K, len-1)]`: out of bounds (a panic upstream) unless K >= len
+  if (!tangent && r.n_elem - 1 >= (uint64_t)k) return ENTERP_INVALID_ARGUMENT;
+  Replica* rp = nullptr;
+  enterp_status st = get_replica(c, device, &rp);
+  if (st) return st;
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  cudaError_t e;
+  if (r.scalar == ENTERP_F32)
+    e = launch_bezier_deriv<float>(r.dim, make_dev<float>(*c, *rp), batch_src<float>(t_dev, n), (int)k, tangent,
+                                   static_cast<float*>(out_dev), static_cast<cudaStream_t>(stream));
+  else
+    e = launch_bezier_deriv<double>(r.dim, make_dev<double>(*c, *rp), batch_src<double>(t_dev, n), (int)k, tangent,
+                                    static_cast<double*>(out_dev), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bezier derivative launch");
+  return ENTERP_OK;
+}
+
+ENTERP_API enterp_status enterp_bezier_tangent_batch(enterp_curve* c, int device, const void* t_dev, uint64_t n,
+                                                     void* out_dev, void* stream) {
+  return bezier_deriv_common(c, device, t_dev, n, 2, 1, out_dev, stream);
+}
+
+ENTERP_API enterp_status enterp_bezier_derivatives_batch(enterp_curve* c, int device, const void* t_dev, uint64_t n,
+                                                         uint32_t k, void* out_dev, void* stream) {
+  return bezier_deriv_common(c, device, t_dev, n, k, 0, out_dev, stream);
+}
+
 ENTERP_API enterp_status enterp_sample_host(enterp_curve* c, int device, const void* t_host, uint64_t n, void* out_host) {
   return host_common(c, device, false, t_host, 0, 0, n, out_host);
 }

@@ -71,6 +71,18 @@ static cudaError_t launch_many_impl(int dim, int n, const R* ctrl, unsigned long
   return cudaErrorInvalidValue;
 }
 
+template <class R>
+static cudaError_t launch_deriv_impl(int dim, const CurveDev<R>& c, const SampleSrc<R>& s, int K, int tangent, R* out,
+                                     cudaStream_t st) {
+  switch (dim) {
+    case 1: return launch_grid_stride(bezier_deriv_kernel<R, 1>, s.count, BLOCK, st, c, s, K, tangent, out);
+    case 2: return launch_grid_stride(bezier_deriv_kernel<R, 2>, s.count, BLOCK, st, c, s, K, tangent, out);
+    case 3: return launch_grid_stride(bezier_deriv_kernel<R, 3>, s.count, BLOCK, st, c, s, K, tangent, out);
+    case 4: return launch_grid_stride(bezier_deriv_kernel<R, 4>, s.count, BLOCK, st, c, s, K, tangent, out);
+  }
+  return cudaErrorInvalidValue;
+}
+
 #define ENTERP_SPECIALIZE(R)                                                                                           \
   template <>                                                                                                          \
   cudaError_t launch_linear<R>(int dh, bool proj, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,      \
@@ -81,6 +93,11 @@ static cudaError_t launch_many_impl(int dim, int n, const R* ctrl, unsigned long
   cudaError_t launch_span<R>(int kind, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, uint32_t* idx,          \
                              R* factor, cudaStream_t st) {                                                             \
     return launch_span_impl<R>(kind, equi, c, s, idx, factor, st);                                                     \
+  }                                                                                                                    \
+  template <>                                                                                                          \
+  cudaError_t launch_bezier_deriv<R>(int dim, const CurveDev<R>& c, const SampleSrc<R>& s, int K, int tangent, R* out, \
+                                     cudaStream_t st) {                                                                \
+    return launch_deriv_impl<R>(dim, c, s, K, tangent, out, st);                                                       \
   }                                                                                                                    \
   template <>                                                                                                          \
   cudaError_t launch_stepper<R>(const SampleSrc<R>& s, R* out, cudaStream_t st) {                                      \

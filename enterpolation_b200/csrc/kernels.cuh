@@ -645,6 +645,75 @@ __global__ void __launch_bounds__(BLOCK) bezier_many_kernel(const R* __restrict_
 }
 
 // =================================================================================================
+// Bezier::gen_with_tangent / gen_with_deriatives::<K> (bezier/mod.rs:96-153, 270-285), restated as
+// written upstream: the k-th derivative is prod(len-k..len) * (k-th forward difference) of the control
+// polygon after len-1-k folding steps, EXCEPT that the highest one (k == min(K, len-1)) is taken from the
+// still-zeroed output array and is therefore always zero; K <= len-1 panics upstream (host rejects it).
+// Not a throughput path: runtime sizes, workspace in local memory. out [n][K][D].
+// =================================================================================================
+constexpr int MAX_DERIV_N = 64;
+
+template <class R, int D>
+__global__ void __launch_bounds__(BLOCK) bezier_deriv_kernel(const CurveDev<R> c, const SampleSrc<R> s, int K, int tangent,
+                                                             R* __restrict__ out) {
+  const int len = (int)c.n_elem;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; i < s.count;
+       i += (unsigned long long)gridDim.x * BLOCK) {
+    const R x = sample_param(s, i);
+    R ws[MAX_DERIV_N * D];
+    R grad[MAX_DERIV_N * D];
+    for (int m = 0; m < len * D; ++m) ws[m] = __ldg(c.elems + m);
+    auto fold = [&](int count) {  // one triangle_folding_inline step over the first `count` + 1 points
+      const R omx = xsub(R(1), x);
+      for (int j = 0; j < count; ++j)
+#pragma unroll
+        for (int q = 0; q < D; ++q) ws[j * D + q] = merge1(ws[j * D + q], ws[(j + 1) * D + q], x, omx);
+    };
+    R* o = out + i * (unsigned long long)K * D;
+    if (tangent) {  // bezier_with_tangent, K == 2
+      if (len < 2) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+          o[q] = ws[q];
+          o[D + q] = xmul(ws[q], R(0));
+        }
+        continue;
+      }
+      for (int k = 1; k <= len - 2; ++k) fold(len - k);
+      const R scale = from_index((unsigned long long)(len - 1), R(0));
+      const R omx = xsub(R(1), x);
+#pragma unroll
+      for (int q = 0; q < D; ++q) {
+        o[D + q] = xmul(xsub(ws[D + q], ws[q]), scale);
+        o[q] = merge1(ws[q], ws[D + q], x, omx);
+      }
+      continue;
+    }
+    const int deg = K < len - 1 ? K : len - 1;
+    for (int k = 1; k <= len - deg - 1; ++k) fold(len - k);
+    for (int m = 0; m < K; ++m)
+#pragma unroll
+      for (int q = 0; q < D; ++q) grad[m * D + q] = xmul(ws[q], R(0));
+    for (int k = deg; k >= 1; --k) {
+      for (int st = 1; st <= k; ++st)  // lower_triangle_folding_inline(grad[..=k], second - first, k)
+        for (int j = st; j <= k; ++j)
+#pragma unroll
+          for (int q = 0; q < D; ++q) grad[j * D + q] = xsub(grad[j * D + q], grad[(j - 1) * D + q]);
+      unsigned long long prod = 1;
+      for (int f = len - k; f < len; ++f) prod *= (unsigned long long)f;
+      const R pr = from_index(prod, R(0));
+#pragma unroll
+      for (int q = 0; q < D; ++q) grad[k * D + q] = xmul(grad[k * D + q], pr);
+      fold(len - 1);  // "one step of the normal folding" over the whole slice
+      for (int j = 0; j < k; ++j)
+#pragma unroll
+        for (int q = 0; q < D; ++q) grad[j * D + q] = ws[j * D + q];
+    }
+    for (int m = 0; m < K * D; ++m) o[m] = grad[m];
+  }
+}
+
+// =================================================================================================
 // Parity / debug kernels: span decision only, and the stepper values.
 // kind: 0 linear, 1 bezier, 2 bspline
 // =================================================================================================

@@ -63,6 +63,10 @@ cudaError_t launch_bezier_many(int dim, int n, const R* ctrl, unsigned long long
 template <class R>
 cudaError_t launch_span(int kind, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, uint32_t* idx, R* factor,
                         cudaStream_t st);
+// Bezier::gen_with_tangent (tangent = 1, K = 2) / gen_with_deriatives::<K>
+template <class R>
+cudaError_t launch_bezier_deriv(int dim, const CurveDev<R>& c, const SampleSrc<R>& s, int K, int tangent, R* out,
+                                cudaStream_t st);
 template <class R>
 cudaError_t launch_stepper(const SampleSrc<R>& s, R* out, cudaStream_t st);
 

@@ -170,6 +170,30 @@ class Curve:
         _check(self._lib, self._lib.enterp_span_take(self._h, dev, n_total, first, count, idx.data_ptr(), fac.data_ptr(), s))
         return idx, fac
 
+    def gen_with_tangent(self, t):
+        """`Bezier::gen_with_tangent` (bezier/mod.rs:270-276) for every parameter of `t` (CUDA tensor or
+        array-like): returns [n][2][dim] = (value, tangent)."""
+        return self._derivatives(t, 2, True)
+
+    def gen_with_derivatives(self, t, k: int):
+        """`Bezier::gen_with_deriatives::<K>` (bezier/mod.rs:279-285): [n][k][dim]."""
+        return self._derivatives(t, int(k), False)
+
+    def _derivatives(self, t, k, tangent):
+        import torch
+        host = not (hasattr(t, "is_cuda") and t.is_cuda)
+        tt = torch.as_tensor(np.ascontiguousarray(np.asarray(t, dtype=self.dtype)).reshape(-1)).cuda(self.device) if host else t
+        dev = tt.device.index
+        n = tt.numel()
+        out = torch.empty((n, k, self.dim), dtype=self._torch_dtype(), device=tt.device)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        if tangent:
+            st = self._lib.enterp_bezier_tangent_batch(self._h, dev, tt.data_ptr(), n, out.data_ptr(), s)
+        else:
+            st = self._lib.enterp_bezier_derivatives_batch(self._h, dev, tt.data_ptr(), n, k, out.data_ptr(), s)
+        _check(self._lib, st)
+        return out.cpu().numpy() if host else out
+
     def invalid_count(self, device=None) -> int:
         """How many samples so far would have made the reference panic (written as NaN)."""
         dev = self.device if device is None else device

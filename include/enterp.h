@@ -199,6 +199,16 @@ ENTERP_API enterp_status enterp_bezier_many_take(int scalar, int dim, uint64_t n
                                                  uint32_t samples_per_curve, int device,
                                                  void* out_dev, void* stream);
 
+/* Bezier::gen_with_tangent (bezier/mod.rs:270-276): out_dev [n][2][dim] = (value, tangent) per parameter, and
+ * Bezier::gen_with_deriatives::<K> (279-285): out_dev [n][k][dim] = (value, 1st, .., (k-1)-th derivative),
+ * bug-for-bug as upstream (the min(k, n_elements-1)-th entry is always zero). Plain Bezier curves only
+ * (unweighted, `.normalized()`): anything else returns ENTERP_UNSUPPORTED. k < n_elements indexes out of
+ * bounds upstream (a panic) and returns ENTERP_INVALID_ARGUMENT; n_elements, k <= 64. */
+ENTERP_API enterp_status enterp_bezier_tangent_batch(enterp_curve* curve, int device, const void* t_dev, uint64_t n,
+                                                     void* out_dev, void* stream);
+ENTERP_API enterp_status enterp_bezier_derivatives_batch(enterp_curve* curve, int device, const void* t_dev,
+                                                         uint64_t n, uint32_t k, void* out_dev, void* stream);
+
 /* ---- evaluation with HOST buffers (the call a user of the reference makes) ----------------- */
 
 /* `curve.sample(t).collect::<Vec<_>>()`: pageable or pinned host in/out, chunked and pipelined

@@ -53,6 +53,10 @@ struct Vec {
     for (int i = 0; i < D; ++i) a.v[i] = a.v[i] + b.v[i];
     return a;
   }
+  friend Vec operator-(Vec a, const Vec& b) {
+    for (int i = 0; i < D; ++i) a.v[i] = a.v[i] - b.v[i];
+    return a;
+  }
   friend Vec operator*(Vec a, R s) {
     for (int i = 0; i < D; ++i) a.v[i] = a.v[i] * s;
     return a;
@@ -430,6 +434,43 @@ struct Bezier {
     out[1] = R(1);
   }
 };
+
+// bezier/mod.rs:58-70 (lower_triangle_folding_inline), 96-116 (bezier_with_tangent), 122-153
+// (bezier_with_deriatives) — restated as written upstream, including that the highest derivative
+// (k == deg) is taken from the still-zeroed `grad` and therefore always comes out as zero, and that
+// K <= len - 1 indexes out of bounds (a panic upstream, `Panic` here).
+template <class R, class T>
+inline void bezier_with_tangent(std::vector<T>& ws, R x, T out[2]) {
+  const size_t len = ws.size();
+  if (len < 2) {
+    out[0] = ws[0];
+    out[1] = ws[0] * R(0);
+    return;
+  }
+  for (size_t k = 1; k <= len - 2; ++k)
+    for (size_t i = 0; i < len - k; ++i) ws[i] = merge(ws[i], ws[i + 1], x);
+  const T tangent = (ws[1] - ws[0]) * from_usize<R>(len - 1);
+  out[0] = merge(ws[0], ws[1], x);
+  out[1] = tangent;
+}
+template <class R, class T>
+inline void bezier_with_derivatives(std::vector<T>& ws, R x, size_t K, T* grad) {
+  const size_t len = ws.size();
+  const size_t deg = std::min(K, len - 1);
+  for (size_t k = 1; k <= len - deg - 1; ++k)
+    for (size_t i = 0; i < len - k; ++i) ws[i] = merge(ws[i], ws[i + 1], x);
+  for (size_t i = 0; i < K; ++i) grad[i] = ws[0] * R(0);
+  for (size_t k = deg; k >= 1; --k) {
+    if (k >= K) throw Panic{};  // `&mut grad[..=k]` out of range
+    for (size_t s = 1; s <= k; ++s)          // lower_triangle_folding_inline(grad[..=k], second - first, k)
+      for (size_t i = s; i <= k; ++i) grad[i] = grad[i] - grad[i - 1];
+    size_t prod = 1;
+    for (size_t q = len - k; q < len; ++q) prod *= q;
+    grad[k] = grad[k] * from_usize<R>(prod);
+    for (size_t i = 0; i < len - 1; ++i) ws[i] = merge(ws[i], ws[i + 1], x);  // one normal folding step
+    for (size_t i = 0; i < k; ++i) grad[i] = ws[i];
+  }
+}
 
 // bspline/mod.rs:126-133 (workspace), 145-169 (eval), 180-185 (domain), 254 (degree).
 template <class K, class E, class S>

@@ -244,6 +244,8 @@ struct CurveIface {
   virtual uint64_t take(size_t n_total, size_t first, size_t count, void* out) const = 0;
   virtual uint64_t span_many(const void* t, size_t n, uint32_t* idx, void* factor) const = 0;
   virtual uint64_t span_take(size_t n_total, size_t first, size_t count, uint32_t* idx, void* factor) const = 0;
+  // Bezier::gen_with_tangent / gen_with_deriatives::<K> (bezier/mod.rs:270-285); -1 when this is not a plain Bezier
+  virtual int64_t derivatives_many(const void*, size_t, size_t, bool, void*) const { return -1; }
 };
 
 template <class R, int D>
@@ -282,7 +284,7 @@ inline void span_of(const TransformInput<G>& c, typename G::R x, uint32_t& idx, 
 }
 
 template <class C, class R, int D>
-struct CurveImpl final : CurveIface {
+struct CurveImpl : CurveIface {
   C curve;
   explicit CurveImpl(const C& c) : curve(c) {}
   void domain(double out[2]) const override {
@@ -419,9 +421,43 @@ struct Adapted final : CurveIface {
   }
 };
 
+// Plain (unweighted, untransformed) Bezier: adds the derivative entry points.
+template <class R, int D, class E, class S>
+struct BezierImpl final : CurveImpl<Bezier<R, E, S>, R, D> {
+  using Base = CurveImpl<Bezier<R, E, S>, R, D>;
+  explicit BezierImpl(const Bezier<R, E, S>& c) : Base(c) {}
+  // out [n][K][D]; tangent: K == 2 through bezier_with_tangent
+  int64_t derivatives_many(const void* t_, size_t n, size_t K, bool tangent, void* out_) const override {
+    using T = Vec<R, D>;
+    const R* t = static_cast<const R*>(t_);
+    R* out = static_cast<R*>(out_);
+    const size_t len = this->curve.elements.len();
+    std::vector<T> ws(len), grad(K);
+    int64_t invalid = 0;
+    for (size_t i = 0; i < n; ++i) {
+      for (size_t q = 0; q < len; ++q) ws[q] = this->curve.elements.eval(q);
+      try {
+        if (tangent)
+          bezier_with_tangent<R, T>(ws, t[i], grad.data());
+        else
+          bezier_with_derivatives<R, T>(ws, t[i], K, grad.data());
+        for (size_t q = 0; q < K; ++q) store<R, D>(grad[q], out + (i * K + q) * D);
+      } catch (const Panic&) {
+        for (size_t q = 0; q < K * D; ++q) out[i * K * D + q] = std::numeric_limits<R>::quiet_NaN();
+        ++invalid;
+      }
+    }
+    return invalid;
+  }
+};
+
 template <class R, int D, class C>
 CurveIface* finish(const C& c) {
   return new CurveImpl<C, R, D>(c);
+}
+template <class R, int D, class S>
+CurveIface* finish(const Bezier<R, SliceChain<Vec<R, D>>, S>& c) {
+  return new BezierImpl<R, D, SliceChain<Vec<R, D>>, S>(c);
 }
 
 // Wrap with Weighted / TransformInput as the builders' build() do
@@ -583,6 +619,9 @@ ORA_API int ora_create(const enterp_curve_desc* desc, void** out, enterp_error_i
   return ENTERP_OK;
 }
 ORA_API void ora_destroy(void* c) { delete static_cast<CurveIface*>(c); }
+ORA_API int64_t ora_bezier_derivatives(void* c, const void* t, uint64_t n, uint64_t k, int tangent, void* out) {
+  return static_cast<CurveIface*>(c)->derivatives_many(t, (size_t)n, (size_t)k, tangent != 0, out);
+}
 // Curve::clamp() / Curve::slice(bounds). The caller keeps `base` alive for the lifetime of the result.
 ORA_API void* ora_clamp(void* base) {
   const CurveIface* b = static_cast<const CurveIface*>(base);

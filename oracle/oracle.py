@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
     L.ora_create.restype = C.c_int
     L.ora_destroy.argtypes = [vp]
     L.ora_destroy.restype = None
+    L.ora_bezier_derivatives.argtypes = [vp, vp, u64, u64, C.c_int, vp]
+    L.ora_bezier_derivatives.restype = C.c_int64
     L.ora_clamp.argtypes = [vp]
     L.ora_clamp.restype = vp
     L.ora_slice.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_double]
@@ -146,6 +148,22 @@ class OracleCurve:
         out = self._out(count)
         inv = lib().ora_take_mt(self._h, n_total, first, count, out.ctypes.data, threads)
         return (self._shape(out), inv) if return_invalid else self._shape(out)
+
+    def gen_with_tangent(self, t):
+        """Bezier::gen_with_tangent (bezier/mod.rs:270-276) for each t -> [n][2][dim]"""
+        return self._deriv(t, 2, True)
+
+    def gen_with_derivatives(self, t, k):
+        """Bezier::gen_with_deriatives::<K> (bezier/mod.rs:279-285) for each t -> [n][k][dim]"""
+        return self._deriv(t, k, False)
+
+    def _deriv(self, t, k, tangent):
+        t = np.ascontiguousarray(np.asarray(t, dtype=self.dtype)).reshape(-1)
+        out = np.empty((t.shape[0], k, self.dim), dtype=self.dtype)
+        rc = lib().ora_bezier_derivatives(self._h, t.ctypes.data, t.shape[0], k, int(tangent), out.ctypes.data)
+        if rc < 0:
+            raise TypeError("derivatives exist for plain Bezier curves only")
+        return out
 
     def span(self, t):
         t = np.ascontiguousarray(np.asarray(t, dtype=self.dtype)).reshape(-1)

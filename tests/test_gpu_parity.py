@@ -434,3 +434,31 @@ def test_degree_limits_and_unsupported():
     b = BSpline.builder().elements(np.zeros(e)).knots(np.arange(e + 63, dtype=np.float64)).dynamic()  # degree 64
     with pytest.raises(Unsupported):
         b.build().sample(np.array([1.0]))
+
+
+# ---- Bezier tangent / derivatives ---------------------------------------------------
+def test_bezier_tangent_reference_kats():  # bezier/mod.rs:345-390
+    c = Bezier.builder().elements([1.0, 2.0, 3.0]).normalized("f64").constant().build()
+    assert c.gen_with_tangent([0.5]).ravel().tolist() == [2.0, 2.0]
+    assert c.gen_with_derivatives([0.5], 3).ravel().tolist() == [2.0, 2.0, 0.0]
+    assert c.gen_with_derivatives([0.5], 5).ravel().tolist() == [2.0, 2.0, 0.0, 0.0, 0.0]
+    one = Bezier.builder().elements([5.0]).normalized("f64").constant().build()
+    assert one.gen_with_tangent([0.25, 0.75]).ravel().tolist() == [5.0, 0.0, 5.0, 0.0]
+    from enterpolation_b200 import InvalidArgument, Unsupported
+    with pytest.raises(InvalidArgument):
+        c.gen_with_derivatives([0.5], 2)  # K <= len - 1 panics upstream
+    with pytest.raises(Unsupported):
+        Linear.builder().elements([0.0, 1.0]).knots([0.0, 1.0]).build().gen_with_tangent([0.5])
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("n,dim", [(1, 1), (2, 3), (3, 2), (5, 4), (16, 3), (33, 1)])
+def test_bezier_derivatives_vs_oracle(scalar, n, dim):
+    dtype = DT[scalar]
+    el = rand_elements(n, dim, dtype, 0xA1 + n)
+    b = Bezier.builder().elements(el).normalized(scalar).constant()
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    t = np.concatenate([np.linspace(-0.5, 1.5, 101), [0.0, 1.0, -0.0]]).astype(dtype)
+    assert_bits_equal(c.gen_with_tangent(t), r.gen_with_tangent(t), f"tangent n={n}")
+    for k in {n, n + 1, n + 3}:
+        assert_bits_equal(c.gen_with_derivatives(t, k), r.gen_with_derivatives(t, k), f"derivatives n={n} K={k}")

@@ -197,3 +197,13 @@ def test_take_shards_agree():
     parts = [c.take(1000, lo, hi - lo) for lo, hi in ((0, 333), (333, 700), (700, 1000))]
     assert np.array_equal(np.concatenate(parts).view(np.uint32), whole.view(np.uint32))
     assert np.array_equal(c.take(1000, threads=3).view(np.uint32), whole.view(np.uint32))
+
+
+def test_bezier_tangent_and_derivatives():  # src/bezier/mod.rs:345-390
+    c = oracle.OracleCurve(Bezier.builder().elements([1.0, 2.0, 3.0]).normalized("f64").constant().to_desc())
+    assert_near(c.gen_with_tangent([0.5]).ravel(), [2.0, 2.0], 4)
+    assert_near(c.gen_with_derivatives([0.5], 3).ravel(), [2.0, 2.0, 0.0], 4)
+    assert_near(c.gen_with_derivatives([0.5], 5).ravel(), [2.0, 2.0, 0.0, 0.0, 0.0], 4)
+    for els in ([5.0],):  # bigger_workspace / constant
+        one = oracle.OracleCurve(Bezier.builder().elements(els).normalized("f64").constant().to_desc())
+        assert_near(one.gen_with_tangent([0.5, 0.25, 0.75]).ravel(), [5.0, 0.0, 5.0, 0.0, 5.0, 0.0], 4)
