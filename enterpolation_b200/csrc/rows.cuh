@@ -224,8 +224,14 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
       } else {
         const T nd = P::make(row[2 * NOPS * W + t * W], row[2 * NOPS * W + t * W + (W - 1)]);
         fac[t] = exact_div<R>(num, y, nd);
-#pragma unroll
-        for (int l = 0; l < W; ++l) fast_ok = fast_ok && in_guard(P::lane(num, l));
+        // Range guard of the exact division with two compares per sample: the left knots of a span are
+        // ascending (kl_0 <= .. <= kl_{p-1}), so x - kl_{p-1} >= 2^-40 bounds every numerator from below
+        // and x - kl_0 <= 2^40 from above. Anything else (x on or left of a knot, far right, NaN, inf)
+        // takes the IEEE division below.
+        constexpr int w_first = sched_find(DEG, W, 1, 0);    // factor (r=1, j=0): numerator x - kl_0
+        constexpr int w_last = sched_find(DEG, W, DEG, 0);   // factor (r=p, j=0): numerator x - kl_{p-1}
+        if (t == (w_first >> 1)) fast_ok = fast_ok && (P::lane(num, w_first & 1) <= P::guard_hi());
+        if (t == (w_last >> 1)) fast_ok = fast_ok && (P::lane(num, w_last & 1) >= P::guard_lo());
       }
     }
     if (!POW2 && !fast_ok) {
