@@ -263,6 +263,8 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   d.eq_first = (R)r.eq_first;
   d.eq_lenm2 = r.inner_len >= 2 ? (R)(r.inner_len - 2) : R(0);  // from_usize(len - 2), list.rs:546
   d.eq_const = r.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT ? 1 : 0;
+  d.eq_mode = r.eq_mode;
+  d.eq_rstep = (R)r.eq_rstep;
   d.n_pre = (int)cv.pre.size();
   for (int i = 0; i < d.n_pre && i < MAX_PRE; ++i) {
     d.pre_kind[i] = cv.pre[i].kind;

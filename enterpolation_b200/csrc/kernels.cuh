@@ -39,6 +39,8 @@ struct CurveDev {
   int32_t map_add;
   R eq_step, eq_offset, eq_first, eq_lenm2;
   int eq_const;  // ConstEquidistant (list.rs:566-721): scaled = x * eq_step with eq_step = fl(N-1), offset 0
+  int eq_mode;   // exact replacement of the divide by eq_step: 0 none, 1 multiply by eq_rstep, 2 exact division
+  R eq_rstep;    // RN(1 / eq_step)
   // input adaptors applied to the raw parameter, outermost first (base/adaptors.rs): Clamp(lo, hi) or the
   // affine map t * a + b of TransformInput / Slice (two roundings, never fused)
   int n_pre;
@@ -146,6 +148,35 @@ __device__ __forceinline__ R sample_param(const SampleSrc<R>& s, unsigned long l
   return xadd(xmul(s.step, from_index(s.first + i, R(0))), s.start);
 }
 
+// ---- exact division by a build-time constant (see rows.cuh header for the argument) ---------------
+__device__ __forceinline__ float xfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double xfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+template <class R>
+__device__ __forceinline__ R exact_div_scalar(R num, R y, R nd) {
+  const R q0 = xmul(num, y);
+  const R r0 = xfma(nd, q0, num);
+  const R q1 = xfma(r0, y, q0);
+  const R r1 = xfma(nd, q1, num);
+  return xfma(r1, y, q1);
+}
+__device__ __forceinline__ bool in_guard(float a) {
+  const float m = fabsf(a);
+  return (m >= 9.094947017729282e-13f) && (m <= 1099511627776.0f);  // [2^-40, 2^40]
+}
+__device__ __forceinline__ bool in_guard(double a) {
+  const double m = fabs(a);
+  return (m >= 4.909093465297727e-91) && (m <= 2.037035976334486e+90);  // [2^-300, 2^300]
+}
+// (x - offset) / step of an Equidistant chain, bit-identical to the IEEE division
+template <class R>
+__device__ __forceinline__ R equi_scaled(const CurveDev<R>& c, R x) {
+  if (c.eq_const) return xmul(x, c.eq_step);
+  const R num = xsub(x, c.eq_offset);
+  if (c.eq_mode == 1) return xmul(num, c.eq_rstep);
+  if (c.eq_mode == 2 && in_guard(num)) return exact_div_scalar<R>(num, c.eq_rstep, -c.eq_step);
+  return xdiv(num, c.eq_step);
+}
+
 // ---- span search -------------------------------------------------------------------------------
 // `floor(scaled).to_usize().unwrap()` (list.rs:456, 486): valid iff 0 <= scaled < 2^64.
 template <class R>
@@ -160,7 +191,7 @@ __device__ __forceinline__ bool equi_inner_index(const CurveDev<R>& c, R x, uint
     idx = c.imin;
     return true;
   }
-  const R scaled = xdiv(xsub(x, c.eq_offset), c.eq_step);
+  const R scaled = equi_scaled(c, x);
   if (!to_usize_ok(scaled)) return false;
   const R fl = floor(scaled);
   if (fl >= R(4294967040.0)) {
@@ -313,30 +344,34 @@ __device__ __forceinline__ bool linear_border(const CurveDev<R>& c, R x, uint32_
   const uint32_t len = c.inner_len;
   if (EQUI) {
     // Equidistant::upper_border (list.rs:532-551) / ConstEquidistant::upper_border (702-720)
-    const R scaled = c.eq_const ? xmul(x, c.eq_step) : xdiv(xsub(x, c.eq_offset), c.eq_step);
+    const R scaled = equi_scaled(c, x);
     if (x < c.eq_offset) {
       imin = 0;
       imax = 1;
       factor = scaled;
       return true;
     }
-    const R cl = ceil(scaled);
-    if (!to_usize_ok(scaled) || !(cl < R(18446744073709551616.0))) {
+    // floor/ceil(scaled).to_usize().unwrap(): both succeed iff 0 <= scaled < 2^64 (floats that large are
+    // integers, so ceil adds nothing)
+    if (!to_usize_ok(scaled)) {
       imin = 0;
       imax = 1;
       factor = qnan(R(0));
       return false;
     }
-    const R fl = floor(scaled);
-    const bool beyond = cl >= R(4294967040.0) || (uint32_t)cl >= len;
-    if (beyond) {
+    const R fl = floor(scaled);            // == trunc(scaled) for scaled >= 0
+    const bool whole = fl == scaled;       // ceil == floor exactly on a knot (then min == max, factor 0)
+    const bool big = fl >= R(4294967040.0);
+    const uint32_t lo = big ? 0xFFFFFFFEu : (uint32_t)fl;
+    const uint32_t hi = whole ? lo : lo + 1u;
+    if (big || hi >= len) {
       imin = len - 2;
       imax = len - 1;
       factor = xsub(scaled, c.eq_lenm2);
     } else {
-      imin = (uint32_t)fl;
-      imax = (uint32_t)cl;
-      factor = xsub(scaled, trunc(scaled));  // Real::fract
+      imin = lo;
+      imax = hi;
+      factor = xsub(scaled, fl);           // Real::fract = self - self.trunc()
     }
     return true;
   } else {
@@ -561,8 +596,16 @@ __global__ void __launch_bounds__(MAX_BLOCK) linear_kernel(const CurveDev<R> c, 
       const R omf = xsub(R(1), f);
       const R* __restrict__ a = c.elems + (size_t)imin * DH;
       const R* __restrict__ b = c.elems + (size_t)imax * DH;
+      if constexpr ((DH * (int)sizeof(R)) % 16 == 0) {
+        R av[DH], bv[DH];  // elements are DH*sizeof(R)-aligned: one or two vector loads each
+        load_vec<DH, (DH * (int)sizeof(R)) % 32 == 0>(a, av);
+        load_vec<DH, (DH * (int)sizeof(R)) % 32 == 0>(b, bv);
 #pragma unroll
-      for (int k = 0; k < DH; ++k) w[k] = merge1(__ldg(a + k), __ldg(b + k), f, omf);
+        for (int k = 0; k < DH; ++k) w[k] = merge1(av[k], bv[k], f, omf);
+      } else {
+#pragma unroll
+        for (int k = 0; k < DH; ++k) w[k] = merge1(__ldg(a + k), __ldg(b + k), f, omf);
+      }
     }
     finish_and_store<R, DH, PROJ>(out, i, w, valid, vec_ok, c.invalid);
   }

@@ -241,16 +241,6 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
   if (equi) {
     const R step = (R)r.eq_step;
     if (!(step > R(0)) || !std::isfinite(step)) return;  // degenerate chains keep the generic kernel
-    if (is_pow2(step) && step >= R(1e-30) && step <= R(1e30)) {
-      r.eq_mode = 1;
-      r.eq_rstep = R(1) / step;
-    } else if (den_in_window(step)) {
-      r.eq_mode = 2;
-      r.eq_rstep = R(1) / step;  // correctly rounded by the host division
-    } else {
-      r.eq_mode = 0;
-      r.eq_rstep = 0;
-    }
   }
   const FactorSched sch = make_sched(p, W);
   const int nops = sch.nops;
@@ -456,6 +446,22 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
     }
   }
 
+  // How the kernels may compute (x - offset) / step exactly without the IEEE divide (rows.cuh header):
+  // 1 = step is a power of two (multiply by the exact inverse), 2 = exact division from RN(1/step).
+  if (d.knot_base == ENTERP_KNOTS_EQUIDISTANT) {
+    const R step = (R)r.eq_step;
+    r.eq_mode = 0;
+    r.eq_rstep = 0;
+    if (step > R(0) && std::isfinite(step)) {
+      if (is_pow2(step) && step >= R(1e-30) && step <= R(1e30)) {
+        r.eq_mode = 1;
+        r.eq_rstep = R(1) / step;
+      } else if (den_in_window(step)) {
+        r.eq_mode = 2;
+        r.eq_rstep = R(1) / step;  // correctly rounded by the host division
+      }
+    }
+  }
   if (d.kind == ENTERP_BSPLINE) build_rows<R>(d, s, r, vk);
   if (d.kind == ENTERP_BSPLINE && s.degree >= 1 && s.degree <= 7) {
     const uint32_t per = 32 / sizeof(R);

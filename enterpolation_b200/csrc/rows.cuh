@@ -101,9 +101,6 @@ struct PK<double> {
   static __device__ __forceinline__ double guard_hi() { return 2.037035976334486e+90; }   // 2^300
 };
 
-__device__ __forceinline__ float xfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ double xfma(double a, double b, double c) { return __fma_rn(a, b, c); }
-
 // Correctly rounded num / den from y = RN(1/den) and nd = -den (see header). Caller guards ranges.
 template <class R>
 __device__ __forceinline__ typename PK<R>::T exact_div(typename PK<R>::T num, typename PK<R>::T y,
@@ -114,19 +111,6 @@ __device__ __forceinline__ typename PK<R>::T exact_div(typename PK<R>::T num, ty
   const typename P::T q1 = P::fma(r0, y, q0);
   const typename P::T r1 = P::fma(nd, q1, num);
   return P::fma(r1, y, q1);
-}
-template <class R>
-__device__ __forceinline__ R exact_div_scalar(R num, R y, R nd) {
-  const R q0 = xmul(num, y);
-  const R r0 = xfma(nd, q0, num);
-  const R q1 = xfma(r0, y, q0);
-  const R r1 = xfma(nd, q1, num);
-  return xfma(r1, y, q1);
-}
-template <class R>
-__device__ __forceinline__ bool in_guard(R a) {
-  const R m = fabs(a);
-  return (m >= PK<R>::guard_lo()) && (m <= PK<R>::guard_hi());
 }
 
 // =================================================================================================
