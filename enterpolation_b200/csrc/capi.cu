@@ -321,7 +321,7 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
       // equidistant knots a span division the kernel can do exactly without the IEEE divide.
       const bool map_simple = (r.imin > 0 && r.imax < r.inner_len) || r.adaptor == AD_NONE;
       const bool eq_ok = !equi || (r.rows_mode == 1 ? r.eq_mode == 1 : r.eq_mode >= 1);
-      if (r.rows_mode && rp.rows && deg > 0 && vec_ok && map_simple && eq_ok && cv.pre.empty() && !g_disable_rows) {
+      if (r.rows_mode && rp.rows && deg > 0 && vec_ok && map_simple && eq_ok && !g_disable_rows) {
         RowsDev<R> rw{};
         rw.table = static_cast<const R*>(rp.rows);
         rw.n_rows = r.rows_n;

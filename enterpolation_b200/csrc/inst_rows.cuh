@@ -5,16 +5,11 @@
 
 namespace enterp {
 
-template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2>
-cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out, const RowsDev<R>& rw, cudaStream_t st) {
-  auto kernel = bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2>;
-  static bool configured = false;  // per instantiation; benign race (idempotent attribute)
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_MAX_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  if (s.count == 0) return cudaSuccess;
+template <class K, class R>
+cudaError_t rows_launch_kernel(K kernel, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, const RowsDev<R>& rw,
+                               cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_MAX_BYTES);
+  if (e != cudaSuccess) return e;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, rw.bytes) != cudaSuccess || per_sm < 1)
     per_sm = 1;
@@ -24,6 +19,29 @@ cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
   kernel<<<grid, BLOCK, rw.bytes, st>>>(c, s, out, rw);
   count_launch();
   return cudaGetLastError();
+}
+
+// Host replica of the panic test of rows_span for one stepper value (same IEEE operations; this file is
+// compiled with -ffp-contract=off): Equidistant::strict_upper_bound_clamped panics unless the parameter is
+// left of the first searched knot or 0 <= (x - offset) / step < 2^64 (list.rs:476-488).
+template <class R>
+bool take_param_valid(const CurveDev<R>& c, const SampleSrc<R>& s, unsigned long long i) {
+  const R prod = s.step * (R)(s.first + i);
+  const R x = prod + s.start;
+  if (x < c.eq_first) return true;
+  const R num = x - c.eq_offset;
+  const R scaled = num / c.eq_step;
+  return scaled >= R(0) && scaled < R(18446744073709551616.0);
+}
+
+template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2>
+cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out, const RowsDev<R>& rw, cudaStream_t st) {
+  if (s.count == 0) return cudaSuccess;
+  if (s.t != nullptr) return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 0>, c, s, out, rw, st);
+  bool need_check = c.n_pre > 0;  // input adaptors ride on the checked variant
+  if (EQUI && !need_check) need_check = !(take_param_valid(c, s, 0) && take_param_valid(c, s, s.count - 1));
+  if (need_check) return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 1>, c, s, out, rw, st);
+  return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 2>, c, s, out, rw, st);
 }
 
 template <class R, int DH, bool PROJ, bool EQUI, bool POW2>

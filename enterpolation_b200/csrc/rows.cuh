@@ -156,6 +156,12 @@ __device__ __forceinline__ uint32_t rows_span(const CurveDev<R>& c, const RowsDe
   return min(inner + rw.ri_off, rw.n_rows - 1u);  // the clamp is a no-op for every valid sample
 }
 
+// Out of line on purpose: the hot kernel must stay small (its adaptor-free loops are I-cache sensitive).
+template <class R>
+__device__ __noinline__ R apply_pre_outlined(const CurveDev<R>& c, R x) {
+  return apply_pre(c, x);
+}
+
 constexpr int ROWS_S = 2;  // samples per thread per loop trip (block-strided, so stores stay coalesced)
 
 template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, bool TAKE, bool CHECK>
@@ -280,9 +286,16 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
     store_elem<R, D>(dst, 0, v, true);
   };
 
+  // Input adaptors (Clamp / Slice / Bezier-style affine maps, base/adaptors.rs) ride on the CHECK variant
+  // only, so the adaptor-free take loop stays as lean as it is.
   auto param = [&](const int slot, const bool active) -> R {
-    if (TAKE) return xadd(xmul(s.step, from_index(gi + (unsigned long long)slot * BLOCK, R(0))), s.start);
-    return active ? __ldcs(tp + slot * BLOCK) : c.eq_first;
+    R x;
+    if (TAKE)
+      x = xadd(xmul(s.step, from_index(gi + (unsigned long long)slot * BLOCK, R(0))), s.start);
+    else
+      x = active ? __ldcs(tp + slot * BLOCK) : c.eq_first;
+    if (CHECK && c.n_pre) x = apply_pre_outlined(c, x);
+    return x;
   };
 
   uint32_t k = 0;
@@ -319,33 +332,21 @@ __host__ __device__ constexpr int rows_min_blocks(int P, int DH) {
   return row_len<R>(P, DH) * (int)(sizeof(R) / 4) <= 40 ? 4 : 1;
 }
 
-template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2>
-__global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH)) bspline_rows_kernel(const CurveDev<R> c, const SampleSrc<R> s,
-                                                             R* __restrict__ out, const RowsDev<R> rw) {
+// VARIANT: 0 = batch (parameters read from memory, per-sample panic checks), 1 = take with per-sample
+// checks and input adaptors, 2 = take, check-free (the host has proven that no sample of the launch can
+// make the reference panic: t_i = step*fl(i)+start is monotone in i and the set of parameters the
+// reference accepts is an interval unbounded below, so it suffices that both ends of the launch's range
+// are valid). Three kernels rather than three paths in one: the hot loop is I-cache sensitive.
+template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, int VARIANT>
+__global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH)) bspline_rows_kernel(const CurveDev<R> c,
+                                                                                         const SampleSrc<R> s,
+                                                                                         R* __restrict__ out,
+                                                                                         const RowsDev<R> rw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   tma_stage(smem_raw, rw.table, rw.bytes, &mbar);
   const R* __restrict__ tab = reinterpret_cast<const R*>(smem_raw);
-  if (s.t) {
-    rows_body<R, DH, PROJ, DEG, EQUI, POW2, false, true>(c, s, out, rw, tab);
-    return;
-  }
-  // take(): t_i = step*fl(i)+start is monotone in i and the set of parameters the reference accepts is an
-  // interval unbounded below, so the launch needs per-sample panic checks only if one of its two end
-  // points fails (NaN step of take(1), a range running past 2^64 knot steps, ...).
-  bool need_check = false;
-  if (EQUI) {
-    bool v0, v1;
-    const R x0 = xadd(xmul(s.step, from_index(s.first, R(0))), s.start);
-    const R x1 = xadd(xmul(s.step, from_index(s.first + s.count - 1, R(0))), s.start);
-    rows_span<R, EQUI, POW2, true>(c, rw, x0, v0);
-    rows_span<R, EQUI, POW2, true>(c, rw, x1, v1);
-    need_check = !(v0 && v1);
-  }
-  if (need_check)
-    rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, true>(c, s, out, rw, tab);
-  else
-    rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, false>(c, s, out, rw, tab);
+  rows_body<R, DH, PROJ, DEG, EQUI, POW2, VARIANT != 0, VARIANT != 2>(c, s, out, rw, tab);
 }
 
 }  // namespace enterp
