@@ -193,8 +193,6 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
       all.insert(all.end(), c->core->r.levels.level[l].begin(), c->core->r.levels.level[l].end());
     }
     e = put(all, &rp->pyramid);
-    // Stage everything above the bottom level in shared memory when that is big enough to fall out of
-    // L1 (small pyramids stay L1-resident anyway) and small enough to fit.
     // Stage as many top levels as fit the per-CTA budget in shared memory (two fat CTAs per SM). Small
     // trees stay in L1 on their own; only trees whose upper levels exceed ~8 KB are worth staging.
     int n_top = 0;
