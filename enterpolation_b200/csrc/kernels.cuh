@@ -97,6 +97,7 @@ __device__ __forceinline__ R merge1(R a, R b, R f, R omf) {
 // TransformInput::eval: input * multiplication + addition (adaptors.rs:141-152).
 template <class R>
 __device__ __forceinline__ R apply_pre(const CurveDev<R>& c, R x) {
+  if (c.n_pre == 0) return x;  // uniform: one branch instead of MAX_PRE predicated slots
 #pragma unroll
   for (int i = 0; i < MAX_PRE; ++i) {
     if (i < c.n_pre) {

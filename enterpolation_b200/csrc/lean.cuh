@@ -1,0 +1,131 @@
+// Lean `Curve::take(n)` kernels (signal.rs:221-228) for the two curve families whose generic kernels are
+// bound by instruction issue rather than by HBM: Linear over Equidistant / ConstEquidistant knots
+// (linear/mod.rs:122-128, list.rs:532-551, 702-720) and single Bezier curves (bezier/mod.rs:44-56).
+//
+// ncu on the generic kernels (profiles/README.md, "lean take"): 127 and 118 warp instructions per sample at
+// 83 % / 77 % issue utilisation, most of them uniform bookkeeping — adaptor slots, easing dispatch, batch-or-take
+// selection, 64-bit index arithmetic with I2F.U64 on the XU pipe, the panic test of `to_usize().unwrap()`,
+// and (Bezier) one scalar LDG per control value per sample. The launchers in inst_lean.cuh check on the host,
+// with the same IEEE operations the device uses, that a given take() needs none of that:
+//   * stepper source (no parameter array), no input adaptor (Bezier: at most one affine map), no easing,
+//     16-byte aligned output, global sample indices below 2^32 - 2^24 (I2FP.F32.U32 instead of I2F.U64);
+//   * Linear: eq_step > 0, stepper step >= 0 (so x_i, x_i - offset and the quotient are monotone in i), the first
+//     parameter is not left of the first knot and the last quotient is below 2^32 - 256 — hence no sample of the
+//     launch can take the `x < offset` exit, fail `to_usize`, or overflow the 32-bit index.
+// Everything else falls back to the generic kernels, which stay the reference-complete path.
+// Arithmetic is the same sequence of IEEE operations as kernels.cuh (same helpers), so results are bit-identical.
+#pragma once
+#include "kernels.cuh"
+
+namespace enterp {
+
+__device__ __forceinline__ float from_u32(uint32_t i, float) { return __uint2float_rn(i); }
+__device__ __forceinline__ double from_u32(uint32_t i, double) { return __uint2double_rn(i); }
+
+template <class R>
+struct LeanTake {
+  R step, start;    // t_i = step * fl(first + i) + start (list.rs:416-418)
+  uint32_t first;   // global index of sample 0 of this launch
+  uint32_t count;   // samples of this launch; first + count <= 2^32 - 2^24
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Linear over (Const)Equidistant knots. MODE selects how (x - offset) / step is formed, all bit-identical to the
+// IEEE quotient: 0 ConstEquidistant (x * fl(N-1), list.rs:702-720), 1 multiply by the exact inverse (power-of-two
+// step), 2 reciprocal + FMA correction inside the guard window with an IEEE fallback, 3 IEEE divide.
+// ---------------------------------------------------------------------------------------------------------------
+template <class R>
+struct LeanLinear {
+  const R* elems;  // [len][DH]
+  uint32_t len;
+  R eq_step, eq_offset, eq_rstep, eq_lenm2;
+};
+
+template <class R, int MODE>
+__device__ __forceinline__ R lean_scaled(const LeanLinear<R>& c, R x) {
+  if constexpr (MODE == 0) {
+    return xmul(x, c.eq_step);
+  } else {
+    const R num = xsub(x, c.eq_offset);
+    if constexpr (MODE == 1) return xmul(num, c.eq_rstep);
+    if constexpr (MODE == 2) {
+      if (in_guard(num)) return exact_div_scalar<R>(num, c.eq_rstep, -c.eq_step);
+    }
+    return xdiv(num, c.eq_step);
+  }
+}
+
+template <class R, int DH, bool PROJ, int MODE>
+__global__ void __launch_bounds__(BLOCK) linear_equi_take_kernel(const LeanLinear<R> c, const LeanTake<R> s,
+                                                                 R* __restrict__ out) {
+  const uint32_t stride = gridDim.x * BLOCK;
+  for (uint32_t i = blockIdx.x * BLOCK + threadIdx.x; i < s.count; i += stride) {
+    const R x = xadd(xmul(s.step, from_u32(s.first + i, R(0))), s.start);
+    const R scaled = lean_scaled<R, MODE>(c, x);
+    // Equidistant::upper_border (list.rs:532-551) with 0 <= scaled < 2^32 - 256 guaranteed by the launcher
+    const R fl = floor(scaled);
+    const uint32_t lo = (uint32_t)fl;
+    const uint32_t hi = fl == scaled ? lo : lo + 1u;  // ceil == floor exactly on a knot
+    const bool last = hi >= c.len;
+    const uint32_t imin = last ? c.len - 2u : lo;
+    const uint32_t imax = last ? c.len - 1u : hi;
+    const R f = xsub(scaled, last ? c.eq_lenm2 : fl);
+    const R omf = xsub(R(1), f);
+    const R* __restrict__ a = c.elems + (size_t)imin * DH;
+    const R* __restrict__ b = c.elems + (size_t)imax * DH;
+    R w[DH];
+    if constexpr ((DH * (int)sizeof(R)) % 16 == 0) {
+      R av[DH], bv[DH];
+      load_vec<DH, (DH * (int)sizeof(R)) % 32 == 0>(a, av);
+      load_vec<DH, (DH * (int)sizeof(R)) % 32 == 0>(b, bv);
+#pragma unroll
+      for (int k = 0; k < DH; ++k) w[k] = merge1(av[k], bv[k], f, omf);
+    } else {
+#pragma unroll
+      for (int k = 0; k < DH; ++k) w[k] = merge1(__ldg(a + k), __ldg(b + k), f, omf);
+    }
+    constexpr int D = PROJ ? DH - 1 : DH;
+    R v[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = PROJ ? xdiv(w[k], w[DH - 1]) : w[k];  // Homogeneous::project
+    store_elem<R, D>(out, i, v, true);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bezier: the control values travel in the kernel parameter block (constant bank), so the first de Casteljau
+// level reads them as instruction operands and no load is issued per sample.
+// ---------------------------------------------------------------------------------------------------------------
+template <class R, int NV>
+struct LeanBezier {
+  int affine;   // TransformInput of Bezier .domain(a, b) (adaptors.rs:141-152): x * aff_a + aff_b, two roundings
+  R aff_a, aff_b;
+  R el[NV];     // [N][DH], homogeneous-lifted when weighted
+};
+
+template <class R, int DH, bool PROJ, int N>
+__global__ void __launch_bounds__(BLOCK) bezier_take_kernel(const LeanBezier<R, N * DH> c, const LeanTake<R> s,
+                                                            R* __restrict__ out) {
+  const uint32_t stride = gridDim.x * BLOCK;
+  for (uint32_t i = blockIdx.x * BLOCK + threadIdx.x; i < s.count; i += stride) {
+    R x = xadd(xmul(s.step, from_u32(s.first + i, R(0))), s.start);
+    if (c.affine) x = xadd(xmul(x, c.aff_a), c.aff_b);
+    const R omx = xsub(R(1), x);
+    R ws[N * DH];
+#pragma unroll
+    for (int m = 0; m < N * DH; ++m) ws[m] = c.el[m];
+#pragma unroll
+    for (int k = 1; k <= N - 1; ++k)
+#pragma unroll
+      for (int j = 0; j < N - k; ++j)
+#pragma unroll
+        for (int q = 0; q < DH; ++q) ws[j * DH + q] = merge1(ws[j * DH + q], ws[(j + 1) * DH + q], x, omx);
+    constexpr int D = PROJ ? DH - 1 : DH;
+    R v[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = PROJ ? xdiv(ws[k], ws[DH - 1]) : ws[k];
+    store_elem<R, D>(out, i, v, true);
+  }
+}
+
+}  // namespace enterp

@@ -462,3 +462,58 @@ def test_bezier_derivatives_vs_oracle(scalar, n, dim):
     assert_bits_equal(c.gen_with_tangent(t), r.gen_with_tangent(t), f"tangent n={n}")
     for k in {n, n + 1, n + 3}:
         assert_bits_equal(c.gen_with_derivatives(t, k), r.gen_with_derivatives(t, k), f"derivatives n={n} K={k}")
+
+
+# ---- lean take kernels (csrc/lean.cuh): host-verified preconditions, else the generic kernels ---------------
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("dim,weighted", [(1, 0), (2, 0), (3, 0), (4, 0), (1, 1), (3, 1), (4, 1)])
+@pytest.mark.parametrize("knots_kind", ["domain", "normalized_pow2", "normalized", "distance", "tiny_step", "const"])
+def test_lean_linear_take(scalar, dim, weighted, knots_kind):
+    """take() of Linear over equidistant knots: every division mode of the lean kernel, whole takes, windows with
+    a global offset, and windows past the 32-bit index limit (which must fall back to the generic kernel)."""
+    dtype = DT[scalar]
+    e = 33 if knots_kind == "normalized_pow2" else 37
+    el = rand_elements(e, dim, dtype, 0xE1 + dim)
+    if knots_kind == "const":
+        if weighted:
+            pytest.skip("equidistant_unchecked takes plain elements")
+        b = Linear.equidistant_unchecked(el, scalar)
+    else:
+        b = Linear.builder()
+        b = b.elements_with_weights(el, (0.5 + u01(e, 0xE3, dtype)).astype(dtype)) if weighted else b.elements(el)
+        b = b.equidistant(scalar)
+        b = {"domain": lambda: b.domain(-1.0, 4.0), "normalized": lambda: b.normalized(),
+             "normalized_pow2": lambda: b.normalized(), "distance": lambda: b.distance(2.0, 0.125),
+             "tiny_step": lambda: b.distance(0.0, 3e-30 if scalar == "f32" else 3e-250)}[knots_kind]()
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    for n in (2, 3, 36, 37, 255, 257, 100003):
+        assert_bits_equal(c.take_device(n).cpu().numpy(), r.take(n), f"{knots_kind} take {n}")
+    total = 100003 + 54321
+    assert_bits_equal(c.take_device(total, 777, 100003).cpu().numpy(), r.take(total, 777, 100003), "take window")
+    n_total = (1 << 32) + 12345
+    for first in (0, (1 << 31) + 17, (1 << 32) - (1 << 24) - 3000, (1 << 32) - 1500, n_total - 3000):
+        assert_bits_equal(c.take_device(n_total, first, 3000).cpu().numpy(), r.take(n_total, first, 3000),
+                          f"{knots_kind} first={first}")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("dim,weighted,domain", [(1, 0, None), (2, 0, (-3.0, 5.0)), (3, 0, None), (4, 0, None),
+                                                 (1, 1, None), (3, 1, (1.0, 3.0)), (4, 1, None)])
+def test_lean_bezier_take(scalar, n, dim, weighted, domain):
+    dtype = DT[scalar]
+    el = rand_elements(n, dim, dtype, 0xF1 + n)
+    b = Bezier.builder()
+    b = b.elements_with_weights(el, (0.5 + u01(n, 0xF3, dtype)).astype(dtype)) if weighted else b.elements(el)
+    b = b.domain(domain[0], domain[1], scalar) if domain else b.normalized(scalar)
+    b = b.constant()
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    for cnt in (2, 33, 256, 100003):
+        assert_bits_equal(c.take_device(cnt).cpu().numpy(), r.take(cnt), f"bezier take {cnt}")
+    n_total = (1 << 32) + 12345
+    for first in (5, (1 << 32) - (1 << 24) - 2000, (1 << 32) - 1000):
+        assert_bits_equal(c.take_device(n_total, first, 2500).cpu().numpy(), r.take(n_total, first, 2500), f"first={first}")
+    # a sliced Bezier carries two affine maps: generic kernel
+    lo, hi = (0.25, 0.75) if domain is None else (domain[0] + 0.5, domain[1] - 0.5)
+    s, rs = c.slice(lo, hi), r.slice(lo, hi)
+    assert_bits_equal(s.take_device(1001).cpu().numpy(), rs.take(1001), "sliced bezier take")
