@@ -341,13 +341,13 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
       break;
     }
     case ENTERP_LINEAR:
-      if (equi && !g_disable_lean && lean_linear_take<R>(r.dh, proj, d, s, static_cast<R*>(out), vec_ok, st, &e)) break;
+      if (equi && !g_disable_lean && lean_linear<R>(r.dh, proj, d, s, static_cast<R*>(out), vec_ok, st, &e)) break;
       e = launch_linear<R>(r.dh, proj, equi, d, s, static_cast<R*>(out), vec_ok, st);
       break;
     default: {
       if (r.n_elem > (uint64_t)MAX_DYN_BEZIER) return ENTERP_UNSUPPORTED;
       const int n = r.n_elem <= 16 ? (int)r.n_elem : 0;
-      if (!g_disable_lean && lean_bezier_take<R>(r.dh, proj, n, reinterpret_cast<const R*>(r.elems.data()), d, s,
+      if (!g_disable_lean && lean_bezier<R>(r.dh, proj, n, reinterpret_cast<const R*>(r.elems.data()), d, s,
                                                  static_cast<R*>(out), vec_ok, st, &e))
         break;
       e = launch_bezier<R>(r.dh, proj, n, d, s, static_cast<R*>(out), vec_ok, st);

@@ -1,5 +1,5 @@
-// Launchers of the lean take kernels (lean.cuh) for one scalar type R: verify the preconditions on the host,
-// pick the instantiation, launch. Each returns false (nothing launched) when the take() does not qualify.
+// Launchers of the lean kernels (lean.cuh) for one (scalar type R, batch-or-take): verify the preconditions on
+// the host, pick the instantiation, launch. Each returns false (nothing launched) when the call does not qualify.
 #pragma once
 #include <cstring>
 
@@ -10,9 +10,9 @@ namespace enterp {
 
 constexpr unsigned long long LEAN_INDEX_LIMIT = (1ull << 32) - (1ull << 24);  // headroom for the 32-bit grid stride
 
-template <class R>
-bool lean_take_src(const SampleSrc<R>& s, bool vec_ok, LeanTake<R>& t) {
-  if (s.t != nullptr || !vec_ok || s.count == 0) return false;
+template <class R, bool BATCH>
+bool lean_src(const SampleSrc<R>& s, bool vec_ok, LeanTake<R>& t) {
+  if ((s.t != nullptr) != BATCH || !vec_ok || s.count == 0) return false;
   if (s.first + s.count > LEAN_INDEX_LIMIT) return false;
   t.step = s.step;
   t.start = s.start;
@@ -28,29 +28,38 @@ R lean_param(const LeanTake<R>& t, uint32_t i) {
   return prod + t.start;
 }
 
-template <class R, int DH, bool PROJ>
-cudaError_t lean_linear_pick(int mode, const LeanLinear<R>& c, const LeanTake<R>& t, R* out, cudaStream_t st) {
+template <class R, int DH, bool PROJ, bool EASE, bool BATCH>
+cudaError_t lean_linear_pick_mode(int mode, const LeanLinear<R>& c, const LeanTake<R>& t, const R* ts, R* out,
+                                  cudaStream_t st) {
   switch (mode) {
-    case 0: return launch_grid_stride(linear_equi_take_kernel<R, DH, PROJ, 0>, t.count, BLOCK, st, c, t, out);
-    case 1: return launch_grid_stride(linear_equi_take_kernel<R, DH, PROJ, 1>, t.count, BLOCK, st, c, t, out);
-    case 2: return launch_grid_stride(linear_equi_take_kernel<R, DH, PROJ, 2>, t.count, BLOCK, st, c, t, out);
-    default: return launch_grid_stride(linear_equi_take_kernel<R, DH, PROJ, 3>, t.count, BLOCK, st, c, t, out);
+    case 0: return launch_grid_stride(linear_equi_lean_kernel<R, DH, PROJ, 0, EASE, BATCH>, t.count, BLOCK, st, c, t, ts, out);
+    case 1: return launch_grid_stride(linear_equi_lean_kernel<R, DH, PROJ, 1, EASE, BATCH>, t.count, BLOCK, st, c, t, ts, out);
+    case 2: return launch_grid_stride(linear_equi_lean_kernel<R, DH, PROJ, 2, EASE, BATCH>, t.count, BLOCK, st, c, t, ts, out);
+    default: return launch_grid_stride(linear_equi_lean_kernel<R, DH, PROJ, 3, EASE, BATCH>, t.count, BLOCK, st, c, t, ts, out);
   }
 }
 
-template <class R>
-bool lean_linear_take_impl(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
-                           cudaStream_t st, cudaError_t* err) {
+template <class R, int DH, bool PROJ, bool BATCH>
+cudaError_t lean_linear_pick(int mode, const LeanLinear<R>& c, const LeanTake<R>& t, const R* ts, R* out, cudaStream_t st) {
+  if (c.easing) return lean_linear_pick_mode<R, DH, PROJ, true, BATCH>(mode, c, t, ts, out, st);
+  return lean_linear_pick_mode<R, DH, PROJ, false, BATCH>(mode, c, t, ts, out, st);
+}
+
+template <class R, bool BATCH>
+bool lean_linear_impl(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
+                      cudaStream_t st, cudaError_t* err) {
   LeanTake<R> t{};
-  if (!lean_take_src(s, vec_ok, t)) return false;
-  if (c.n_pre != 0 || c.easing != 0 || c.inner_len < 2 || c.inner_len > 0x7fffffffu) return false;
-  if (!(c.eq_step > R(0)) || !(t.step >= R(0))) return false;  // also rejects NaN
+  if (!lean_src<R, BATCH>(s, vec_ok, t)) return false;
+  if (c.n_pre != 0 || c.inner_len < 2 || c.inner_len > 0x7fffffffu) return false;
   const int mode = c.eq_const ? 0 : (c.eq_mode == 1 ? 1 : (c.eq_mode == 2 ? 2 : 3));
-  const R x0 = lean_param(t, 0), x1 = lean_param(t, t.count - 1);
-  const R offset = c.eq_const ? R(0) : c.eq_offset;
-  if (!(x0 >= offset)) return false;
-  const R scaled1 = c.eq_const ? x1 * c.eq_step : (x1 - c.eq_offset) / c.eq_step;
-  if (!(scaled1 >= R(0) && scaled1 < R(4294967040.0))) return false;
+  if (!BATCH) {
+    if (!(c.eq_step > R(0)) || !(t.step >= R(0))) return false;  // also rejects NaN
+    const R x0 = lean_param(t, 0), x1 = lean_param(t, t.count - 1);
+    const R offset = c.eq_const ? R(0) : c.eq_offset;
+    if (!(x0 >= offset)) return false;
+    const R scaled1 = c.eq_const ? x1 * c.eq_step : (x1 - c.eq_offset) / c.eq_step;
+    if (!(scaled1 >= R(0) && scaled1 < R(4294967040.0))) return false;
+  }
   LeanLinear<R> l{};
   l.elems = c.elems;
   l.len = c.inner_len;
@@ -58,20 +67,25 @@ bool lean_linear_take_impl(int dh, bool proj, const CurveDev<R>& c, const Sample
   l.eq_offset = c.eq_offset;
   l.eq_rstep = c.eq_rstep;
   l.eq_lenm2 = c.eq_lenm2;
+  l.easing = c.easing;
+  l.easing_n = c.easing_n;
+  l.ease_min = c.ease_min;
+  l.ease_max = c.ease_max;
+  l.invalid = c.invalid;
   *err = cudaErrorInvalidValue;
   if (!proj) {
     switch (dh) {
-      case 1: *err = lean_linear_pick<R, 1, false>(mode, l, t, out, st); break;
-      case 2: *err = lean_linear_pick<R, 2, false>(mode, l, t, out, st); break;
-      case 3: *err = lean_linear_pick<R, 3, false>(mode, l, t, out, st); break;
-      case 4: *err = lean_linear_pick<R, 4, false>(mode, l, t, out, st); break;
+      case 1: *err = lean_linear_pick<R, 1, false, BATCH>(mode, l, t, s.t, out, st); break;
+      case 2: *err = lean_linear_pick<R, 2, false, BATCH>(mode, l, t, s.t, out, st); break;
+      case 3: *err = lean_linear_pick<R, 3, false, BATCH>(mode, l, t, s.t, out, st); break;
+      case 4: *err = lean_linear_pick<R, 4, false, BATCH>(mode, l, t, s.t, out, st); break;
     }
   } else {
     switch (dh) {
-      case 2: *err = lean_linear_pick<R, 2, true>(mode, l, t, out, st); break;
-      case 3: *err = lean_linear_pick<R, 3, true>(mode, l, t, out, st); break;
-      case 4: *err = lean_linear_pick<R, 4, true>(mode, l, t, out, st); break;
-      case 5: *err = lean_linear_pick<R, 5, true>(mode, l, t, out, st); break;
+      case 2: *err = lean_linear_pick<R, 2, true, BATCH>(mode, l, t, s.t, out, st); break;
+      case 3: *err = lean_linear_pick<R, 3, true, BATCH>(mode, l, t, s.t, out, st); break;
+      case 4: *err = lean_linear_pick<R, 4, true, BATCH>(mode, l, t, s.t, out, st); break;
+      case 5: *err = lean_linear_pick<R, 5, true, BATCH>(mode, l, t, s.t, out, st); break;
     }
   }
   return true;
@@ -79,52 +93,53 @@ bool lean_linear_take_impl(int dh, bool proj, const CurveDev<R>& c, const Sample
 
 constexpr int LEAN_BEZIER_MAX_N = 8;
 
-template <class R, int DH, bool PROJ, int N>
-cudaError_t lean_bezier_launch(const R* host_elems, const CurveDev<R>& c, const LeanTake<R>& t, R* out, cudaStream_t st) {
+template <class R, int DH, bool PROJ, int N, bool BATCH>
+cudaError_t lean_bezier_launch(const R* host_elems, const CurveDev<R>& c, const LeanTake<R>& t, const R* ts, R* out,
+                               cudaStream_t st) {
   LeanBezier<R, N * DH> b{};
   b.affine = c.n_pre;
   b.aff_a = c.n_pre ? c.pre_a[0] : R(1);
   b.aff_b = c.n_pre ? c.pre_b[0] : R(0);
   std::memcpy(b.el, host_elems, sizeof(R) * N * DH);
-  return launch_grid_stride(bezier_take_kernel<R, DH, PROJ, N>, t.count, BLOCK, st, b, t, out);
+  return launch_grid_stride(bezier_lean_kernel<R, DH, PROJ, N, BATCH>, t.count, BLOCK, st, b, t, ts, out);
 }
 
-template <class R, int DH, bool PROJ>
-cudaError_t lean_bezier_pick_n(int n, const R* host_elems, const CurveDev<R>& c, const LeanTake<R>& t, R* out,
-                               cudaStream_t st) {
+template <class R, int DH, bool PROJ, bool BATCH>
+cudaError_t lean_bezier_pick_n(int n, const R* host_elems, const CurveDev<R>& c, const LeanTake<R>& t, const R* ts,
+                               R* out, cudaStream_t st) {
   switch (n) {
-    case 2: return lean_bezier_launch<R, DH, PROJ, 2>(host_elems, c, t, out, st);
-    case 3: return lean_bezier_launch<R, DH, PROJ, 3>(host_elems, c, t, out, st);
-    case 4: return lean_bezier_launch<R, DH, PROJ, 4>(host_elems, c, t, out, st);
-    case 5: return lean_bezier_launch<R, DH, PROJ, 5>(host_elems, c, t, out, st);
-    case 6: return lean_bezier_launch<R, DH, PROJ, 6>(host_elems, c, t, out, st);
-    case 7: return lean_bezier_launch<R, DH, PROJ, 7>(host_elems, c, t, out, st);
-    case 8: return lean_bezier_launch<R, DH, PROJ, 8>(host_elems, c, t, out, st);
+    case 2: return lean_bezier_launch<R, DH, PROJ, 2, BATCH>(host_elems, c, t, ts, out, st);
+    case 3: return lean_bezier_launch<R, DH, PROJ, 3, BATCH>(host_elems, c, t, ts, out, st);
+    case 4: return lean_bezier_launch<R, DH, PROJ, 4, BATCH>(host_elems, c, t, ts, out, st);
+    case 5: return lean_bezier_launch<R, DH, PROJ, 5, BATCH>(host_elems, c, t, ts, out, st);
+    case 6: return lean_bezier_launch<R, DH, PROJ, 6, BATCH>(host_elems, c, t, ts, out, st);
+    case 7: return lean_bezier_launch<R, DH, PROJ, 7, BATCH>(host_elems, c, t, ts, out, st);
+    case 8: return lean_bezier_launch<R, DH, PROJ, 8, BATCH>(host_elems, c, t, ts, out, st);
   }
   return cudaErrorInvalidValue;
 }
 
-template <class R>
-bool lean_bezier_take_impl(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c, const SampleSrc<R>& s,
-                           R* out, bool vec_ok, cudaStream_t st, cudaError_t* err) {
+template <class R, bool BATCH>
+bool lean_bezier_impl(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
+                      bool vec_ok, cudaStream_t st, cudaError_t* err) {
   LeanTake<R> t{};
-  if (!lean_take_src(s, vec_ok, t)) return false;
+  if (!lean_src<R, BATCH>(s, vec_ok, t)) return false;
   if (n < 2 || n > LEAN_BEZIER_MAX_N || host_elems == nullptr) return false;
   if (c.n_pre > 1 || (c.n_pre == 1 && c.pre_kind[0] != 1)) return false;
   *err = cudaErrorInvalidValue;
   if (!proj) {
     switch (dh) {
-      case 1: *err = lean_bezier_pick_n<R, 1, false>(n, host_elems, c, t, out, st); break;
-      case 2: *err = lean_bezier_pick_n<R, 2, false>(n, host_elems, c, t, out, st); break;
-      case 3: *err = lean_bezier_pick_n<R, 3, false>(n, host_elems, c, t, out, st); break;
-      case 4: *err = lean_bezier_pick_n<R, 4, false>(n, host_elems, c, t, out, st); break;
+      case 1: *err = lean_bezier_pick_n<R, 1, false, BATCH>(n, host_elems, c, t, s.t, out, st); break;
+      case 2: *err = lean_bezier_pick_n<R, 2, false, BATCH>(n, host_elems, c, t, s.t, out, st); break;
+      case 3: *err = lean_bezier_pick_n<R, 3, false, BATCH>(n, host_elems, c, t, s.t, out, st); break;
+      case 4: *err = lean_bezier_pick_n<R, 4, false, BATCH>(n, host_elems, c, t, s.t, out, st); break;
     }
   } else {
     switch (dh) {
-      case 2: *err = lean_bezier_pick_n<R, 2, true>(n, host_elems, c, t, out, st); break;
-      case 3: *err = lean_bezier_pick_n<R, 3, true>(n, host_elems, c, t, out, st); break;
-      case 4: *err = lean_bezier_pick_n<R, 4, true>(n, host_elems, c, t, out, st); break;
-      case 5: *err = lean_bezier_pick_n<R, 5, true>(n, host_elems, c, t, out, st); break;
+      case 2: *err = lean_bezier_pick_n<R, 2, true, BATCH>(n, host_elems, c, t, s.t, out, st); break;
+      case 3: *err = lean_bezier_pick_n<R, 3, true, BATCH>(n, host_elems, c, t, s.t, out, st); break;
+      case 4: *err = lean_bezier_pick_n<R, 4, true, BATCH>(n, host_elems, c, t, s.t, out, st); break;
+      case 5: *err = lean_bezier_pick_n<R, 5, true, BATCH>(n, host_elems, c, t, s.t, out, st); break;
     }
   }
   return true;
@@ -132,16 +147,16 @@ bool lean_bezier_take_impl(int dh, bool proj, int n, const R* host_elems, const 
 
 }  // namespace enterp
 
-#define ENTERP_DEFINE_LEAN(R)                                                                                          \
+#define ENTERP_DEFINE_LEAN(R, BATCH)                                                                                   \
   namespace enterp {                                                                                                   \
   template <>                                                                                                          \
-  bool lean_linear_take<R>(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,        \
-                           cudaStream_t st, cudaError_t* err) {                                                        \
-    return lean_linear_take_impl<R>(dh, proj, c, s, out, vec_ok, st, err);                                             \
+  bool lean_linear_part<R, BATCH>(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok, \
+                                  cudaStream_t st, cudaError_t* err) {                                                 \
+    return lean_linear_impl<R, BATCH>(dh, proj, c, s, out, vec_ok, st, err);                                           \
   }                                                                                                                    \
   template <>                                                                                                          \
-  bool lean_bezier_take<R>(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c, const SampleSrc<R>& s, \
-                           R* out, bool vec_ok, cudaStream_t st, cudaError_t* err) {                                   \
-    return lean_bezier_take_impl<R>(dh, proj, n, host_elems, c, s, out, vec_ok, st, err);                              \
+  bool lean_bezier_part<R, BATCH>(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c,                 \
+                                  const SampleSrc<R>& s, R* out, bool vec_ok, cudaStream_t st, cudaError_t* err) {     \
+    return lean_bezier_impl<R, BATCH>(dh, proj, n, host_elems, c, s, out, vec_ok, st, err);                            \
   }                                                                                                                    \
   }

@@ -1,0 +1,2 @@
+#include "inst_lean.cuh"
+ENTERP_DEFINE_LEAN(float, true)

@@ -57,14 +57,26 @@ cudaError_t launch_linear(int dh, bool proj, bool equi, const CurveDev<R>& c, co
 template <class R>
 cudaError_t launch_bezier(int dh, bool proj, int n, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
                           cudaStream_t st);
-// Lean take kernels (lean.cuh): launch and return true when the take() qualifies (status in *err), else false.
-// host_elems: the curve's lifted control values on the host ([n][dh]).
-template <class R>
-bool lean_linear_take(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok, cudaStream_t st,
+// Lean kernels (lean.cuh): launch and return true when the call qualifies (status in *err), else false.
+// host_elems: the curve's lifted control values on the host ([n][dh]). One translation unit per (R, BATCH).
+template <class R, bool BATCH>
+bool lean_linear_part(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok, cudaStream_t st,
                       cudaError_t* err);
-template <class R>
-bool lean_bezier_take(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
+template <class R, bool BATCH>
+bool lean_bezier_part(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
                       bool vec_ok, cudaStream_t st, cudaError_t* err);
+template <class R>
+inline bool lean_linear(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok, cudaStream_t st,
+                        cudaError_t* err) {
+  return s.t ? lean_linear_part<R, true>(dh, proj, c, s, out, vec_ok, st, err)
+             : lean_linear_part<R, false>(dh, proj, c, s, out, vec_ok, st, err);
+}
+template <class R>
+inline bool lean_bezier(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
+                        bool vec_ok, cudaStream_t st, cudaError_t* err) {
+  return s.t ? lean_bezier_part<R, true>(dh, proj, n, host_elems, c, s, out, vec_ok, st, err)
+             : lean_bezier_part<R, false>(dh, proj, n, host_elems, c, s, out, vec_ok, st, err);
+}
 template <class R>
 cudaError_t launch_bezier_many(int dim, int n, const R* ctrl, unsigned long long n_curves, uint32_t n_ctrl,
                                uint32_t samples, R step, R* out, cudaStream_t st);

@@ -7,11 +7,12 @@
 // selection, 64-bit index arithmetic with I2F.U64 on the XU pipe, the panic test of `to_usize().unwrap()`,
 // and (Bezier) one scalar LDG per control value per sample. The launchers in inst_lean.cuh check on the host,
 // with the same IEEE operations the device uses, that a given take() needs none of that:
-//   * stepper source (no parameter array), no input adaptor (Bezier: at most one affine map), no easing,
-//     16-byte aligned output, global sample indices below 2^32 - 2^24 (I2FP.F32.U32 instead of I2F.U64);
-//   * Linear: eq_step > 0, stepper step >= 0 (so x_i, x_i - offset and the quotient are monotone in i), the first
-//     parameter is not left of the first knot and the last quotient is below 2^32 - 256 — hence no sample of the
-//     launch can take the `x < offset` exit, fail `to_usize`, or overflow the 32-bit index.
+//   * no input adaptor (Bezier: at most one affine map), 16-byte aligned output, sample indices below
+//     2^32 - 2^24 (I2FP.F32.U32 instead of I2F.U64); easing and batch-vs-take are template parameters;
+//   * Linear take(): eq_step > 0, stepper step >= 0 (so x_i, x_i - offset and the quotient are monotone in i), the
+//     first parameter is not left of the first knot and the last quotient is below 2^32 - 256 — hence no sample of
+//     the launch can take the `x < offset` exit, fail `to_usize`, or overflow the 32-bit index. Batches
+//     (`Signal::sample`, arbitrary parameters) keep those tests, as selects.
 // Everything else falls back to the generic kernels, which stay the reference-complete path.
 // Arithmetic is the same sequence of IEEE operations as kernels.cuh (same helpers), so results are bit-identical.
 #pragma once
@@ -21,6 +22,9 @@ namespace enterp {
 
 __device__ __forceinline__ float from_u32(uint32_t i, float) { return __uint2float_rn(i); }
 __device__ __forceinline__ double from_u32(uint32_t i, double) { return __uint2double_rn(i); }
+// saturating conversions (negative / NaN -> 0): defined for every input, unlike the C++ cast
+__device__ __forceinline__ uint32_t to_u32(float v) { return __float2uint_rz(v); }
+__device__ __forceinline__ uint32_t to_u32(double v) { return __double2uint_rz(v); }
 
 template <class R>
 struct LeanTake {
@@ -39,6 +43,10 @@ struct LeanLinear {
   const R* elems;  // [len][DH]
   uint32_t len;
   R eq_step, eq_offset, eq_rstep, eq_lenm2;
+  // easing of the lerp factor (linear/mod.rs:127), EASE kernels only
+  int easing, easing_n;
+  R ease_min, ease_max;
+  unsigned long long* invalid;  // BATCH kernels only: samples where the reference would panic
 };
 
 template <class R, int MODE>
@@ -55,21 +63,54 @@ __device__ __forceinline__ R lean_scaled(const LeanLinear<R>& c, R x) {
   }
 }
 
-template <class R, int DH, bool PROJ, int MODE>
-__global__ void __launch_bounds__(BLOCK) linear_equi_take_kernel(const LeanLinear<R> c, const LeanTake<R> s,
-                                                                 R* __restrict__ out) {
+template <class R>
+__device__ __forceinline__ R lean_easing(const LeanLinear<R>& c, R f) {
+  switch (c.easing) {  // uniform; same expressions as apply_easing (kernels.cuh)
+    case 1: return xsub(R(1), f);
+    case 2: return smoothstart_exact(f, c.easing_n);
+    case 3: return xsub(R(1), smoothstart_exact(xsub(R(1), f), c.easing_n));
+    case 4: return smoothstep_exact(f);
+    case 5: return xmul(xmul(xmul(f, f), f), xadd(xmul(f, xsub(xmul(f, R(6)), R(15))), R(10)));
+    default: {
+      R t;
+      if (f < c.ease_min) t = R(0);
+      else if (f > c.ease_max) t = R(1);
+      else t = xdiv(xsub(f, c.ease_min), xsub(c.ease_max, c.ease_min));
+      return smoothstep_exact(t);
+    }
+  }
+}
+
+// BATCH: parameters come from an array and may be anything, so the kernel keeps the `x < offset` exit and the
+// `to_usize` panic test of upper_border as selects (no divergent branches); otherwise the launcher has proven them
+// unreachable for this take().
+template <class R, int DH, bool PROJ, int MODE, bool EASE, bool BATCH>
+__global__ void __launch_bounds__(BLOCK) linear_equi_lean_kernel(const LeanLinear<R> c, const LeanTake<R> s,
+                                                                 const R* __restrict__ t, R* __restrict__ out) {
   const uint32_t stride = gridDim.x * BLOCK;
   for (uint32_t i = blockIdx.x * BLOCK + threadIdx.x; i < s.count; i += stride) {
-    const R x = xadd(xmul(s.step, from_u32(s.first + i, R(0))), s.start);
+    const R x = BATCH ? __ldcs(t + i) : xadd(xmul(s.step, from_u32(s.first + i, R(0))), s.start);
     const R scaled = lean_scaled<R, MODE>(c, x);
-    // Equidistant::upper_border (list.rs:532-551) with 0 <= scaled < 2^32 - 256 guaranteed by the launcher
+    // Equidistant::upper_border (list.rs:532-551)
     const R fl = floor(scaled);
-    const uint32_t lo = (uint32_t)fl;
+    const bool big = BATCH && fl >= R(4294967040.0);
+    const uint32_t lo = big ? 0xFFFFFFFEu : to_u32(fl);
     const uint32_t hi = fl == scaled ? lo : lo + 1u;  // ceil == floor exactly on a knot
-    const bool last = hi >= c.len;
-    const uint32_t imin = last ? c.len - 2u : lo;
-    const uint32_t imax = last ? c.len - 1u : hi;
-    const R f = xsub(scaled, last ? c.eq_lenm2 : fl);
+    const bool last = big || hi >= c.len;
+    uint32_t imin = last ? c.len - 2u : lo;
+    uint32_t imax = last ? c.len - 1u : hi;
+    R f = xsub(scaled, last ? c.eq_lenm2 : fl);
+    bool valid = true;
+    if constexpr (BATCH) {
+      const bool below = x < (MODE == 0 ? R(0) : c.eq_offset);
+      valid = below || to_usize_ok(scaled);
+      if (below || !valid) {
+        imin = 0;
+        imax = 1;
+        f = scaled;
+      }
+    }
+    if constexpr (EASE) f = lean_easing(c, f);
     const R omf = xsub(R(1), f);
     const R* __restrict__ a = c.elems + (size_t)imin * DH;
     const R* __restrict__ b = c.elems + (size_t)imax * DH;
@@ -88,6 +129,13 @@ __global__ void __launch_bounds__(BLOCK) linear_equi_take_kernel(const LeanLinea
     R v[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) v[k] = PROJ ? xdiv(w[k], w[DH - 1]) : w[k];  // Homogeneous::project
+    if constexpr (BATCH) {
+      if (!valid) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) v[k] = qnan(R(0));
+        atomicAdd(c.invalid, 1ull);
+      }
+    }
     store_elem<R, D>(out, i, v, true);
   }
 }
@@ -103,12 +151,12 @@ struct LeanBezier {
   R el[NV];     // [N][DH], homogeneous-lifted when weighted
 };
 
-template <class R, int DH, bool PROJ, int N>
-__global__ void __launch_bounds__(BLOCK) bezier_take_kernel(const LeanBezier<R, N * DH> c, const LeanTake<R> s,
-                                                            R* __restrict__ out) {
+template <class R, int DH, bool PROJ, int N, bool BATCH>
+__global__ void __launch_bounds__(BLOCK) bezier_lean_kernel(const LeanBezier<R, N * DH> c, const LeanTake<R> s,
+                                                            const R* __restrict__ t, R* __restrict__ out) {
   const uint32_t stride = gridDim.x * BLOCK;
   for (uint32_t i = blockIdx.x * BLOCK + threadIdx.x; i < s.count; i += stride) {
-    R x = xadd(xmul(s.step, from_u32(s.first + i, R(0))), s.start);
+    R x = BATCH ? __ldcs(t + i) : xadd(xmul(s.step, from_u32(s.first + i, R(0))), s.start);
     if (c.affine) x = xadd(xmul(x, c.aff_a), c.aff_b);
     const R omx = xsub(R(1), x);
     R ws[N * DH];

@@ -485,9 +485,21 @@ def test_lean_linear_take(scalar, dim, weighted, knots_kind):
         b = {"domain": lambda: b.domain(-1.0, 4.0), "normalized": lambda: b.normalized(),
              "normalized_pow2": lambda: b.normalized(), "distance": lambda: b.distance(2.0, 0.125),
              "tiny_step": lambda: b.distance(0.0, 3e-30 if scalar == "f32" else 3e-250)}[knots_kind]()
+    if (dim + weighted) % 2 == 0:  # half of the cases carry an easing (EASE instantiations)
+        from enterpolation_b200 import easing as E
+        b = b.easing([E.smoothstep, E.smootherstep, E.Plateau(0.6), E.smoothend(3)][dim - 1])
     c, r = b.build(), oracle.OracleCurve(b.to_desc())
     for n in (2, 3, 36, 37, 255, 257, 100003):
         assert_bits_equal(c.take_device(n).cpu().numpy(), r.take(n), f"{knots_kind} take {n}")
+    # batch (Signal::sample): arbitrary parameters incl. out-of-domain, NaN, inf -> panic counter
+    d = r.domain()
+    t = adversarial(np.linspace(float(d[0]), float(d[1]), 4 * (e - 1) + 1), dtype, np.random.default_rng(dim))
+    t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf], dtype=dtype), u01(100003, 0xE5, dtype) * dtype(d[1] - d[0]) + dtype(d[0])])
+    before = c.invalid_count()
+    got = c.sample_device(torch.from_numpy(t).cuda()).cpu().numpy()
+    want, inv = r.eval(t, return_invalid=True)
+    assert_bits_equal(got, want, f"{knots_kind} batch")
+    assert c.invalid_count() - before == inv and inv >= 1
     total = 100003 + 54321
     assert_bits_equal(c.take_device(total, 777, 100003).cpu().numpy(), r.take(total, 777, 100003), "take window")
     n_total = (1 << 32) + 12345
@@ -510,6 +522,9 @@ def test_lean_bezier_take(scalar, n, dim, weighted, domain):
     c, r = b.build(), oracle.OracleCurve(b.to_desc())
     for cnt in (2, 33, 256, 100003):
         assert_bits_equal(c.take_device(cnt).cpu().numpy(), r.take(cnt), f"bezier take {cnt}")
+    t = np.concatenate([adversarial([0.0, 0.5, 1.0, 2.0, 3.0], dtype, np.random.default_rng(n), n_random=500),
+                        u01(100003, 0xF5, dtype) * dtype(1.5) - dtype(0.25)]).astype(dtype)
+    assert_bits_equal(c.sample_device(torch.from_numpy(t).cuda()).cpu().numpy(), r.eval(t), "bezier batch")
     n_total = (1 << 32) + 12345
     for first in (5, (1 << 32) - (1 << 24) - 2000, (1 << 32) - 1000):
         assert_bits_equal(c.take_device(n_total, first, 2500).cpu().numpy(), r.take(n_total, first, 2500), f"first={first}")

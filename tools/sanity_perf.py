@@ -22,8 +22,12 @@ c = Linear.builder().elements(el4).equidistant("f32").normalized().build()
 timeit(lambda: c.take_device(n, out=out4), n, "Linear equidistant [f32;4] take", 16)
 c = Linear.builder().elements(el4).equidistant("f32").normalized().easing(easing.smoothstep).build()
 timeit(lambda: c.take_device(n, out=out4), n, "Linear equidistant [f32;4] smoothstep take", 16)
+tb = torch.rand(n, device="cuda", dtype=torch.float32)
+c = Linear.builder().elements(el4).equidistant("f32").normalized().build()
+timeit(lambda: c.sample_device(tb, out=out4), n, "Linear equidistant [f32;4] random batch", 20)
 c = Bezier.builder().elements(el4[:4]).normalized("f32").constant().build()
 timeit(lambda: c.take_device(n, out=out4), n, "Bezier cubic [f32;4] take", 16)
+timeit(lambda: c.sample_device(tb, out=out4), n, "Bezier cubic [f32;4] random batch", 20)
 c = Bezier.builder().elements(el4[:8]).normalized("f32").constant().build()
 timeit(lambda: c.take_device(n, out=out4), n, "Bezier degree 7 [f32;4] take", 16)
 w = math.sqrt(2) / 2
