@@ -16,10 +16,11 @@ from .errors import (BezierError, BSplineError, DeviceError, Empty, Enterpolatio
                      InvalidDegree, KnotElementInequality, LinearError, NotSorted, TooFewElements,
                      TooFewKnots, TooSmallWorkspace, Unsupported)
 from .sharding import shard_range, shard_sizes
+from . import serde  # noqa: E402  (imports the builders)
 
 __all__ = [
     "BSpline", "Linear", "Bezier", "BSplineBuilder", "LinearBuilder", "BezierBuilder", "Curve", "Take",
-    "bezier_many_take", "stepper_device", "shard_range", "shard_sizes", "EnterpolationError",
+    "bezier_many_take", "stepper_device", "serde", "easing", "shard_range", "shard_sizes", "EnterpolationError",
     "LinearError", "BezierError", "BSplineError", "TooFewElements", "TooFewKnots",
     "KnotElementInequality", "NotSorted", "IncongruousElementsKnots", "IncongruousElementsDegree",
     "InvalidDegree", "TooSmallWorkspace", "Empty", "InvalidArgument", "Unsupported", "DeviceError",

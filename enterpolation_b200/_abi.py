@@ -33,7 +33,7 @@ KNOTS_SORTED, KNOTS_EQUIDISTANT, KNOTS_CONST_EQUIDISTANT = 0, 1, 2
 EQ_BY_DEGREE, EQ_BY_QUANTITY = 0, 1
 EQ_DOMAIN, EQ_NORMALIZED, EQ_DISTANCE = 0, 1, 2
 SPACE_CONSTANT, SPACE_DYNAMIC, SPACE_WORKSPACE = 0, 1, 2
-INPUT_NORMALIZED, INPUT_DOMAIN = 0, 1
+INPUT_NORMALIZED, INPUT_DOMAIN, INPUT_TRANSFORM = 0, 1, 2
 EASE_IDENTITY, EASE_FLIP, EASE_SMOOTHSTART, EASE_SMOOTHEND, EASE_SMOOTHSTEP, EASE_SMOOTHERSTEP, EASE_PLATEAU = range(7)
 
 NP_DTYPE = {F32: np.float32, F64: np.float64}
@@ -69,9 +69,18 @@ class CurveInfo(C.Structure):
     ]
 
 
+class CurveResolved(C.Structure):
+    _fields_ = [
+        ("eq_len", C.c_uint64), ("eq_step", C.c_double), ("eq_offset", C.c_double),
+        ("has_transform", C.c_int32), ("easing", C.c_int32),
+        ("in_addition", C.c_double), ("in_multiplication", C.c_double),
+        ("space_len", C.c_uint64), ("ease_min", C.c_double), ("ease_max", C.c_double),
+    ]
+
+
 # every symbol include/enterp.h declares (tests check the built library exports all of them)
 EXPORTS = [
-    "enterp_curve_validate", "enterp_curve_create", "enterp_curve_destroy", "enterp_curve_get_info", "enterp_curve_domain",
+    "enterp_curve_validate", "enterp_curve_create", "enterp_curve_destroy", "enterp_curve_get_info", "enterp_curve_get_resolved", "enterp_curve_domain",
     "enterp_curve_clamp", "enterp_curve_slice", "enterp_curve_upload", "enterp_eval_batch", "enterp_eval_take", "enterp_span_batch",
     "enterp_span_take", "enterp_stepper", "enterp_bezier_many_take", "enterp_bezier_tangent_batch", "enterp_bezier_derivatives_batch", "enterp_sample_host",
     "enterp_take_host", "enterp_host_alloc", "enterp_host_free", "enterp_invalid_count",
@@ -107,6 +116,8 @@ def load_library() -> C.CDLL:
     lib.enterp_curve_destroy.restype = None
     lib.enterp_curve_get_info.argtypes = [vp, C.POINTER(CurveInfo)]
     lib.enterp_curve_get_info.restype = i32
+    lib.enterp_curve_get_resolved.argtypes = [vp, C.POINTER(CurveResolved)]
+    lib.enterp_curve_get_resolved.restype = i32
     lib.enterp_curve_domain.argtypes = [vp, C.POINTER(C.c_double * 2)]
     lib.enterp_curve_domain.restype = i32
     lib.enterp_curve_clamp.argtypes = [vp, C.POINTER(vp)]
@@ -165,7 +176,7 @@ class DescArrays:
 
 def make_desc(kind, scalar, elements, weights=None, *, mode=OPEN, knots=None, equidistant=None,
               space=(SPACE_DYNAMIC, 0), bezier_domain=None, easing=(EASE_IDENTITY, 0, 0.0),
-              const_equidistant=False) -> DescArrays:
+              const_equidistant=False, bezier_transform=None) -> DescArrays:
     """Flatten one finished builder chain into the C descriptor.
 
     elements: array-like [n] or [n][dim]; weights: [n] or None; knots: [k] or None;
@@ -212,4 +223,7 @@ def make_desc(kind, scalar, elements, weights=None, *, mode=OPEN, knots=None, eq
     if bezier_domain is not None:
         d.input_form = INPUT_DOMAIN
         d.in_a, d.in_b = float(dt(bezier_domain[0])), float(dt(bezier_domain[1]))
+    if bezier_transform is not None:  # stored TransformInput { addition, multiplication }
+        d.input_form = INPUT_TRANSFORM
+        d.in_a, d.in_b = float(dt(bezier_transform[0])), float(dt(bezier_transform[1]))
     return DescArrays(d, keep)

@@ -63,6 +63,7 @@ class _Chain:
         self._eq = None           # [eq_by, eq_count, eq_form, a, b]
         self._space = (_abi.SPACE_DYNAMIC, 0)
         self._bezier_domain = None
+        self._bezier_transform = None  # stored TransformInput fields of a deserialised curve (serde.py)
         self._easing = (_abi.EASE_IDENTITY, 0, 0.0)
         self._const_equidistant = False
         self._device = 0
@@ -85,7 +86,7 @@ class _Chain:
                               [] if self._elements is None else self._elements, self._weights,
                               mode=self._mode, knots=self._knots, equidistant=eq, space=self._space,
                               bezier_domain=self._bezier_domain, easing=self._easing,
-                              const_equidistant=self._const_equidistant)
+                              const_equidistant=self._const_equidistant, bezier_transform=self._bezier_transform)
 
     def _validate(self, stage: int):
         """Ask the C library whether the chain so far is valid (Director semantics)."""

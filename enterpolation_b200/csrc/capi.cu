@@ -587,6 +587,23 @@ ENTERP_API enterp_status enterp_curve_slice(const enterp_curve* base, int has_st
   return ENTERP_OK;
 }
 
+ENTERP_API enterp_status enterp_curve_get_resolved(const enterp_curve* c, enterp_curve_resolved* out) {
+  if (!c || !out) return ENTERP_INVALID_ARGUMENT;
+  const Resolved& r = c->core->r;
+  const bool equi = r.kind != ENTERP_BEZIER && r.knot_base != ENTERP_KNOTS_SORTED;
+  out->eq_len = equi ? r.inner_len : 0;
+  out->eq_step = equi ? r.eq_step : 0.0;
+  out->eq_offset = equi ? r.eq_offset : 0.0;
+  out->has_transform = r.has_transform;
+  out->easing = r.easing;
+  out->in_addition = r.in_add;
+  out->in_multiplication = r.in_mul;
+  out->space_len = r.space_len;
+  out->ease_min = r.ease_min;
+  out->ease_max = r.ease_max;
+  return ENTERP_OK;
+}
+
 ENTERP_API enterp_status enterp_curve_get_info(const enterp_curve* c, enterp_curve_info* info) {
   if (!c || !info) return ENTERP_INVALID_ARGUMENT;
   const Resolved& r = c->core->r;

@@ -172,7 +172,7 @@ Fail check_space(const enterp_curve_desc& d, Shape& s) {
   if (d.kind == ENTERP_LINEAR) return ok();
   if (d.space < ENTERP_SPACE_CONSTANT || d.space > ENTERP_SPACE_WORKSPACE) return fail(ENTERP_INVALID_ARGUMENT);
   if (d.kind == ENTERP_BEZIER) {
-    if (d.input_form != ENTERP_INPUT_NORMALIZED && d.input_form != ENTERP_INPUT_DOMAIN) return fail(ENTERP_INVALID_ARGUMENT);
+    if (d.input_form < ENTERP_INPUT_NORMALIZED || d.input_form > ENTERP_INPUT_TRANSFORM) return fail(ENTERP_INVALID_ARGUMENT);
     if (d.space == ENTERP_SPACE_WORKSPACE) {
       // src/bezier/builder.rs:354-367 — the error is built with swapped arguments (line 359)
       if (d.workspace_n < e) return fail(ENTERP_TOO_SMALL_WORKSPACE, e, d.workspace_n);
@@ -310,12 +310,14 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
   if (d.kind == ENTERP_BEZIER) {
     r.domain[0] = 0.0;
     r.domain[1] = 1.0;
-    if (d.input_form == ENTERP_INPUT_DOMAIN) {
+    if (d.input_form != ENTERP_INPUT_NORMALIZED) {
       // TransformInput::normalized_to_domain (src/base/adaptors.rs:137-139) and its domain()
       // (161-166): note t -> t * 1/(end-start) + (-start), only "right" for start == 0.
+      // INPUT_TRANSFORM: the two stored fields verbatim (adaptors.rs:113-117).
+      const bool verbatim = d.input_form == ENTERP_INPUT_TRANSFORM;
       const R start = (R)d.in_a, end = (R)d.in_b;
-      const R add = -start;
-      const R mul = R(1) / (end - start);
+      const R add = verbatim ? (R)d.in_a : -start;
+      const R mul = verbatim ? (R)d.in_b : R(1) / (end - start);
       r.has_transform = 1;
       r.in_add = add;
       r.in_mul = mul;

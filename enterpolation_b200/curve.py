@@ -73,6 +73,13 @@ class Curve:
         _check(self._lib, self._lib.enterp_curve_domain(self._h, C.byref(d)))
         return [self.dtype(d[0]), self.dtype(d[1])]
 
+    def resolved(self) -> _abi.CurveResolved:
+        """Constants the reference's built types carry as fields (Equidistant step/offset, TransformInput
+        addition/multiplication, Plateau min/max, workspace length) — see enterpolation_b200.serde."""
+        r = _abi.CurveResolved()
+        _check(self._lib, self._lib.enterp_curve_get_resolved(self._h, C.byref(r)))
+        return r
+
     @property
     def degree(self) -> int:
         return int(self.info.degree)

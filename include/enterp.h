@@ -76,7 +76,7 @@ enum { ENTERP_KNOTS_SORTED = 0, ENTERP_KNOTS_EQUIDISTANT = 1, ENTERP_KNOTS_CONST
 enum { ENTERP_EQ_BY_DEGREE = 0, ENTERP_EQ_BY_QUANTITY = 1 };                   /* desc.eq_by     */
 enum { ENTERP_EQ_DOMAIN = 0, ENTERP_EQ_NORMALIZED = 1, ENTERP_EQ_DISTANCE = 2 }; /* desc.eq_form */
 enum { ENTERP_SPACE_CONSTANT = 0, ENTERP_SPACE_DYNAMIC = 1, ENTERP_SPACE_WORKSPACE = 2 }; /* desc.space */
-enum { ENTERP_INPUT_NORMALIZED = 0, ENTERP_INPUT_DOMAIN = 1 };                 /* desc.input_form (Bezier) */
+enum { ENTERP_INPUT_NORMALIZED = 0, ENTERP_INPUT_DOMAIN = 1, ENTERP_INPUT_TRANSFORM = 2 };  /* desc.input_form (Bezier) */
 /* desc.easing (Linear): the built-in easing functions of src/easing/mod.rs:86-132 and plateau.rs:10-57
  * applied to the lerp factor (linear/mod.rs:127). Arbitrary closures (FuncEase) cannot cross to the device. */
 enum { ENTERP_EASE_IDENTITY = 0, ENTERP_EASE_FLIP = 1, ENTERP_EASE_SMOOTHSTART = 2, ENTERP_EASE_SMOOTHEND = 3,
@@ -105,7 +105,9 @@ typedef struct enterp_curve_desc {
   double eq_a, eq_b; /* carried as f64; converted to R exactly when R = f32 values were given */
 
   int32_t space;        /* .constant::<N>() | .dynamic() | .workspace(S): BSpline and Bezier */
-  int32_t input_form;   /* Bezier: .normalized::<R>() | .domain(in_a, in_b) (TransformInput) */
+  int32_t input_form;   /* Bezier: .normalized::<R>() | .domain(in_a, in_b) (TransformInput::normalized_to_domain) |
+                           TRANSFORM: a stored TransformInput { addition = in_a, multiplication = in_b } taken verbatim
+                           (base/adaptors.rs:113-117; what a deserialised curve carries) */
   uint64_t workspace_n; /* N of constant::<N>() / S.len() of workspace(S); ignored for dynamic */
   double in_a, in_b;
 
@@ -137,6 +139,19 @@ typedef struct enterp_curve_info {
   double domain[2];      /* Curve::domain() */
 } enterp_curve_info;
 
+/* Constants the reference's built types carry as fields and the builders computed (their serde form,
+ * e.g. src/base/list.rs:354-358, src/base/adaptors.rs:113-117, src/base/space.rs:70-73, src/easing/plateau.rs:10-13):
+ * everything a host wrapper needs to write a built curve back out in the reference's own layout. */
+typedef struct enterp_curve_resolved {
+  uint64_t eq_len;          /* innermost Equidistant { len, step, offset }; 0 when the knots are not equidistant */
+  double eq_step, eq_offset;
+  int32_t has_transform;    /* Bezier .domain(a, b): TransformInput { addition, multiplication } */
+  int32_t easing;           /* ENTERP_EASE_* */
+  double in_addition, in_multiplication;
+  uint64_t space_len;       /* DynSpace { len } / workspace length; N of ConstSpace */
+  double ease_min, ease_max; /* Plateau { min, max } */
+} enterp_curve_resolved;
+
 /* ---- construction: *::builder()...build() ------------------------------------------------- */
 
 /* Validates the descriptor with the reference's builder rules and resolves it on the host (no CUDA
@@ -152,6 +167,7 @@ ENTERP_API enterp_status enterp_curve_create(const enterp_curve_desc* desc, ente
                                              enterp_error_info* err /* may be NULL */);
 ENTERP_API void enterp_curve_destroy(enterp_curve* curve);
 ENTERP_API enterp_status enterp_curve_get_info(const enterp_curve* curve, enterp_curve_info* info);
+ENTERP_API enterp_status enterp_curve_get_resolved(const enterp_curve* curve, enterp_curve_resolved* out);
 /* Curve::domain(): linear/mod.rs:139-141, bspline/mod.rs:180-185, bezier/mod.rs:257-259,
  * base/adaptors.rs:161-166 (TransformInput). */
 ENTERP_API enterp_status enterp_curve_domain(const enterp_curve* curve, double out[2]);

@@ -468,10 +468,14 @@ CurveIface* wrap(const Resolved& r, const C& c) {
     Weighted<C> w{c};
     if (r.kind == ENTERP_BEZIER && r.input_form == ENTERP_INPUT_DOMAIN)
       return finish<R, D>(TransformInput<Weighted<C>>::normalized_to_domain(w, (R)r.in_a, (R)r.in_b));
+    if (r.kind == ENTERP_BEZIER && r.input_form == ENTERP_INPUT_TRANSFORM)  // stored fields, adaptors.rs:113-117
+      return finish<R, D>(TransformInput<Weighted<C>>{w, (R)r.in_a, (R)r.in_b});
     return finish<R, D>(w);
   } else {
     if (r.kind == ENTERP_BEZIER && r.input_form == ENTERP_INPUT_DOMAIN)
       return finish<R, D>(TransformInput<C>::normalized_to_domain(c, (R)r.in_a, (R)r.in_b));
+    if (r.kind == ENTERP_BEZIER && r.input_form == ENTERP_INPUT_TRANSFORM)
+      return finish<R, D>(TransformInput<C>{c, (R)r.in_a, (R)r.in_b});
     return finish<R, D>(c);
   }
 }
