@@ -33,6 +33,8 @@ UNIT = "samples/s"
 # FP-pipe issue peaks measured on this pool's B200 with tools/pipebench.cu (profiles/r01_pipebench.json):
 # dependency-free unfused FMUL/FADD chains, whole chip, lane-operations per second.
 FP32_LANE_OPS = 3.45e13
+# ncu --set full, bspline_rows_kernel<float,4,0,3,1,1,2>, 2^30-sample launch: (17.120574e9 + 250.88e3) B / 2^30 samples
+NCU_C5_DRAM_BYTES_PER_SAMPLE = (17.120574e9 + 250.88e3) / (1 << 30)
 FP64_LANE_OPS = 1.80e13
 
 
@@ -433,6 +435,20 @@ def time_steps(w, steps, warmup, stream, barrier):
     return e0.elapsed_time(e1)
 
 
+def bind_to_gpu_numa(index: int) -> bool:
+    """One process per GPU: run on the cores NVML reports as local to that GPU, so that the pinned host buffers
+    of the end-to-end leg are first touched (and therefore placed) on the GPU's own NUMA node. Without it every
+    rank's device->host stream converges on whichever node the scheduler picked. Not applied at N = 1, where
+    rank 0 also times the all-cores CPU baseline."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return True
+    except Exception:
+        return False
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -444,6 +460,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    numa_bound = world > 1 and bind_to_gpu_numa(local)  # before any allocation: pinned pages land next to the GPU
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
@@ -520,7 +537,7 @@ def run_gpu(args):
     per_launch_ms = ms / args.steps  # rank 0's kernel: one launch per step
     achieved = w.samples * w.bytes_per_sample / (per_launch_ms * 1e-3) / 1e9
     cpu_1t = cpu_all = None
-    if rank == 0:
+    if rank == 0 and world == 1:  # the CPU baseline is an N = 1 leg (at N > 1 the ranks are bound to GPU-local cores)
         cpu_1t = w.cpu_rate(1, 1 << 22)
         cpu_all = w.cpu_rate(cores, 1 << 25)
     c5_samples = w.samples
@@ -550,7 +567,7 @@ def run_gpu(args):
                                 "frac": own * x.fp_ops_per_sample / x.fp_peak,
                                 "peak_source": "tools/pipebench.cu unfused FMUL/FADD (DMUL/DADD) chains, profiles/r01_pipebench.json"},
                 }
-                if rank == 0:
+                if rank == 0 and world == 1:
                     entry["cpu_baseline"] = {"single_thread": x.cpu_rate(1, 1 << 20), "all_cores": x.cpu_rate(cores, 1 << 23),
                                              "cores": cores, "unit": UNIT, "kind": "port"}
                 extra[x.key] = entry
@@ -575,15 +592,22 @@ def run_gpu(args):
                     "what": f"builder.build() + enterp_take_host over a {e2e_total}-sample window of the "
                             f"2^{args.log2_samples} take (pinned host buffer, chunked kernel/D2H pipeline), "
                             f"{e2e_steps} steps, wall clock max over ranks"},
-            "gpu_launches": total_launches,
+            "gpu_launches": total_launches, "numa_bound": bool(numa_bound),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": rows_kernel,
+                         # ncu --set full of this kernel on a 2^30-sample launch (profiles/r01_ncu_c5_rows_final.txt):
+                         # dram__bytes_write.sum 17.12 GB + dram__bytes_read.sum 0.25 MB = 15.95 B/sample, scaled
+                         # to this launch's sample count
+                         "traffic": c5_samples * NCU_C5_DRAM_BYTES_PER_SAMPLE / 1e9, "traffic_unit": "GB per launch",
+                         "traffic_source": "profiles/r01_ncu_c5_rows_final.txt (per-sample DRAM bytes of a 2^30-sample "
+                                           "launch x this launch's samples)",
+                         "kernel": rows_kernel,
                          "algorithmic_bytes_per_sample": 16, "peak_source": f"MEASURED_PEAKS.json ({how}, burst copy)",
                          "fp32_pipe_frac": c5_samples * 125 / (per_launch_ms * 1e-3) / FP32_LANE_OPS},
             "cpu_baseline": {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
                              "single_thread": cpu_1t,
                              "sample": f"{1 << 25} consecutive samples (all cores) / {1 << 22} (1 thread) from the middle of the take; "
-                                       "C++ restatement of enterpolation 0.3.0 (oracle/), per-eval heap workspace as DynSpace"},
+                                       "C++ restatement of enterpolation 0.3.0 (oracle/), per-eval heap workspace as DynSpace"}
+            if world == 1 else None,
             "configs": extra,
         }
         emit(line)
