@@ -1,24 +1,38 @@
 // Span-row B-spline kernel instantiations for one (scalar type, division mode, projection, knot base).
 #pragma once
+#include <cstdlib>
+
 #include "inst_common.cuh"
 #include "rows.cuh"
 
 namespace enterp {
 
+// smem: dynamic shared memory of the launch (the staged row table; 0 for the global-rows variant)
 template <class K, class R>
 cudaError_t rows_launch_kernel(K kernel, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, const RowsDev<R>& rw,
-                               cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_MAX_BYTES);
-  if (e != cudaSuccess) return e;
+                               size_t smem, cudaStream_t st) {
+  if (smem > 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_MAX_BYTES);
+    if (e != cudaSuccess) return e;
+  }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, rw.bytes) != cudaSuccess || per_sm < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, smem) != cudaSuccess || per_sm < 1)
     per_sm = 1;
   const unsigned long long want = (s.count + ROWS_S * BLOCK - 1) / (ROWS_S * BLOCK);
   const unsigned long long cap = (unsigned long long)per_sm * (unsigned long long)sm_count();
   const int grid = (int)(want < cap ? want : cap);
-  kernel<<<grid, BLOCK, rw.bytes, st>>>(c, s, out, rw);
+  kernel<<<grid, BLOCK, smem, st>>>(c, s, out, rw);
   count_launch();
   return cudaGetLastError();
+}
+
+// Ablation switch (env ENTERP_ROWS_CHUNK=1): every check-free take() through the chunked global-rows variant.
+inline bool rows_force_chunk() {
+  static const bool v = [] {
+    const char* e = std::getenv("ENTERP_ROWS_CHUNK");
+    return e && e[0] == '1';
+  }();
+  return v;
 }
 
 // Host replica of the panic test of rows_span for one stepper value (same IEEE operations; this file is
@@ -37,11 +51,23 @@ bool take_param_valid(const CurveDev<R>& c, const SampleSrc<R>& s, unsigned long
 template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2>
 cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out, const RowsDev<R>& rw, cudaStream_t st) {
   if (s.count == 0) return cudaSuccess;
-  if (s.t != nullptr) return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 0>, c, s, out, rw, st);
+  const bool fits = rw.bytes <= ROWS_MAX_BYTES;  // bigger tables serve the global-rows take variant only
   bool need_check = c.n_pre > 0;  // input adaptors ride on the checked variant
-  if (EQUI && !need_check) need_check = !(take_param_valid(c, s, 0) && take_param_valid(c, s, s.count - 1));
-  if (need_check) return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 1>, c, s, out, rw, st);
-  return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 2>, c, s, out, rw, st);
+  if (s.t == nullptr && EQUI && !need_check)
+    need_check = !(take_param_valid(c, s, 0) && take_param_valid(c, s, s.count - 1));
+  // Check-free take(): the chunked variant (rows from global memory, span computation skipped while the stepper
+  // stays inside the cached row's hold interval) wins wherever the span computation is not nearly free — sorted
+  // knots (a pivot search), exact-division rows (C1: 205 vs 182 G samples/s) — and is the only one for tables
+  // beyond the shared-memory budget. Power-of-two equidistant rows that fit (C5) measure the same either way
+  // (309 vs 307 G samples/s at 2^32, 261 vs 268 at 2^24) and keep the shared-memory variant.
+  if (s.t == nullptr && !need_check && (!EQUI || !POW2 || !fits || rows_force_chunk()))
+    return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 3>, c, s, out, rw, 0, st);
+  if (!fits) return cudaErrorNotSupported;  // the caller falls back to the generic kernel
+  if (s.t != nullptr)
+    return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 0>, c, s, out, rw, rw.bytes, st);
+  if (need_check)
+    return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 1>, c, s, out, rw, rw.bytes, st);
+  return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 2>, c, s, out, rw, rw.bytes, st);
 }
 
 template <class R, int DH, bool PROJ, bool EQUI, bool POW2>

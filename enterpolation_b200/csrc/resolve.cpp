@@ -227,6 +227,40 @@ bool den_in_window(R v) {
 }
 
 // Span rows (see rows_layout.hpp): one row per span index in [lo, hi].
+// Monotone integer key of a float (ordered like the floats themselves; -0 and +0 share key 0).
+template <class R>
+struct FloatKey;
+template <>
+struct FloatKey<float> {
+  using I = int64_t;
+  static I key(float v) {
+    int32_t i;
+    std::memcpy(&i, &v, 4);
+    return i >= 0 ? (I)i : -(I)(i & 0x7fffffff);
+  }
+  static float value(I k) {
+    const uint32_t u = k >= 0 ? (uint32_t)k : (0x80000000u | (uint32_t)(-k));
+    float v;
+    std::memcpy(&v, &u, 4);
+    return v;
+  }
+};
+template <>
+struct FloatKey<double> {
+  using I = int64_t;
+  static I key(double v) {
+    int64_t i;
+    std::memcpy(&i, &v, 8);
+    return i >= 0 ? i : -(I)(i & 0x7fffffffffffffffll);
+  }
+  static double value(I k) {
+    const uint64_t u = k >= 0 ? (uint64_t)k : (0x8000000000000000ull | (uint64_t)(-k));
+    double v;
+    std::memcpy(&v, &u, 8);
+    return v;
+  }
+};
+
 template <class R>
 void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R* vk) {
   r.rows_mode = 0;
@@ -235,9 +269,9 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
   const uint64_t lo = s.degree, hi = s.virt_len - s.degree;
   const uint64_t n_rows = hi - lo + 1;
   const int W = lanes_of<R>();
-  const int len = row_len<R>(p, r.dh);
-  if (n_rows * (uint64_t)len * sizeof(R) > ROWS_MAX_BYTES) return;
   const bool equi = d.knot_base == ENTERP_KNOTS_EQUIDISTANT;
+  const int len = row_len<R>(p, r.dh);
+  if (n_rows * (uint64_t)len * sizeof(R) > ROWS_GLOBAL_MAX_BYTES) return;
   if (equi) {
     const R step = (R)r.eq_step;
     if (!(step > R(0)) || !std::isfinite(step)) return;  // degenerate chains keep the generic kernel
@@ -269,6 +303,61 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
       }
     for (int i = 0; i <= p; ++i)
       for (int c = 0; c < r.dh; ++c) row[3 * nops * W + i * dhp + c] = el[(idx - p + i) * r.dh + c];
+    if (!equi) {
+      // the search (list.rs:69-86 restricted to [lo, hi]) returns idx exactly for knots[idx-1] <= x < knots[idx];
+      // everything below knots[lo] maps to lo, everything from knots[hi-1] up to hi
+      const R inf = std::numeric_limits<R>::infinity();
+      row[row_hold_off<R>(p, r.dh)] = idx == lo ? -inf : vk[idx - 1];
+      row[row_hold_off<R>(p, r.dh) + 1] = idx == hi ? inf : vk[idx];
+    }
+  }
+  if (equi) {
+    // Equidistant spans come from floor((x - offset) / step), whose switch-over points are NOT the tabulated
+    // knots once rounding is involved. Find them exactly: row_of() replays the kernel's span arithmetic
+    // (rows.cuh rows_span, EQUI; its multiply-by-inverse and reciprocal+FMA forms are bit-identical to this IEEE
+    // division) and is monotone in x for step > 0, so the first float of every row is found by bisection over the
+    // float ordering.
+    using I = typename FloatKey<R>::I;
+    const R step = (R)r.eq_step, offset = (R)r.eq_offset, first = (R)r.eq_first;
+    const uint32_t imin = (uint32_t)r.imin, imax = (uint32_t)r.imax;
+    const uint32_t ri_off = (uint32_t)((int64_t)r.map_add - (int64_t)lo);
+    auto row_of = [&](R x) -> uint32_t {
+      const R num = x - offset;
+      const R scaled = num / step;
+      uint32_t inner;
+      if (x < first) {
+        inner = imin;
+      } else {
+        const uint32_t u = !(scaled >= R(0)) ? 0u : (scaled >= R(4294967295.0) ? 0xFFFFFFFFu : (uint32_t)scaled);
+        inner = (u < imax - 1u ? u : imax - 1u) + 1u;
+      }
+      const uint32_t ri = inner + ri_off;
+      return ri < (uint32_t)n_rows - 1u ? ri : (uint32_t)n_rows - 1u;
+    };
+    const R inf = std::numeric_limits<R>::infinity();
+    const int off = row_hold_off<R>(p, r.dh);
+    I from = FloatKey<R>::key(-std::numeric_limits<R>::max());
+    const I top = FloatKey<R>::key(std::numeric_limits<R>::max());
+    tab[off] = -inf;
+    for (uint64_t rr = 1; rr < n_rows; ++rr) {
+      R bound = inf;  // no finite parameter reaches this row
+      if (row_of(FloatKey<R>::value(top)) >= rr) {
+        I a = from, b = top;  // invariant: row_of(a) < rr (or a == from) <= row_of(b)
+        if (row_of(FloatKey<R>::value(a)) >= rr) {
+          b = a;
+        } else {
+          while ((uint64_t)b - (uint64_t)a > 1) {  // key differences can exceed int64 for doubles
+            const I m = a + (I)(((uint64_t)b - (uint64_t)a) / 2);
+            if (row_of(FloatKey<R>::value(m)) >= rr) b = m; else a = m;
+          }
+        }
+        bound = FloatKey<R>::value(b);
+        from = b;
+      }
+      tab[(rr - 1) * len + off + 1] = bound;
+      tab[rr * len + off] = bound;
+    }
+    tab[(n_rows - 1) * len + off + 1] = inf;
   }
   // mode 1 multiplies by exact inverses everywhere (the equidistant span division included), mode 2
   // divides exactly from tabulated reciprocals; both need the span division to be covered.

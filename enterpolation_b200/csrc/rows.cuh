@@ -164,7 +164,12 @@ __device__ __noinline__ R apply_pre_outlined(const CurveDev<R>& c, R x) {
 
 constexpr int ROWS_S = 2;  // samples per thread per loop trip (block-strided, so stores stay coalesced)
 
-template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, bool TAKE, bool CHECK>
+// CHUNK: every CTA walks ONE contiguous range of tiles instead of striding the whole grid, so a thread's
+// parameter advances by only TILE stepper steps per trip: its span (and the row cached in registers) changes
+// rarely, row reloads can come from global memory / L2 (tables of any size), and the span computation (sorted
+// knots: the pivot search; equidistant: the exact division and floor) is skipped while the parameter stays inside
+// the cached row's [hold_lo, hold_hi) interval, which the host tabulated with the kernel's own arithmetic.
+template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, bool TAKE, bool CHECK, bool CHUNK>
 __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<R>& s, R* __restrict__ out,
                                           const RowsDev<R>& rw, const R* __restrict__ tab) {
   using P = PK<R>;
@@ -173,15 +178,29 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
   constexpr int NOPS = sched_nops(DEG, W);
   constexpr int DHP = round_up(DH, W);
   constexpr int ROW = row_len<R>(DEG, DH);
+  constexpr bool HOLD = CHUNK;
+  constexpr int HOLD_OFF = row_hold_off<R>(DEG, DH);
   constexpr int VEC = 16 / (int)sizeof(R);  // R values per 128-bit shared load
   constexpr int EL0 = 3 * NOPS * W;
   constexpr int D = PROJ ? DH - 1 : DH;
   constexpr unsigned long long TILE = (unsigned long long)ROWS_S * BLOCK;
 
-  const unsigned long long stride = (unsigned long long)gridDim.x * TILE;
-  const unsigned long long block0 = (unsigned long long)blockIdx.x * TILE;
-  if (block0 >= s.count) return;
-  const unsigned long long rest = s.count - block0;
+  unsigned long long stride, block0, rest;
+  if (CHUNK) {
+    const unsigned long long tiles = (s.count + TILE - 1) / TILE;
+    const unsigned long long per = (tiles + gridDim.x - 1) / gridDim.x;
+    const unsigned long long t0 = (unsigned long long)blockIdx.x * per;
+    if (t0 >= tiles) return;
+    const unsigned long long t1 = t0 + per < tiles ? t0 + per : tiles;
+    stride = TILE;
+    block0 = t0 * TILE;
+    rest = (t1 * TILE < s.count ? t1 * TILE : s.count) - block0;
+  } else {
+    stride = (unsigned long long)gridDim.x * TILE;
+    block0 = (unsigned long long)blockIdx.x * TILE;
+    if (block0 >= s.count) return;
+    rest = s.count - block0;
+  }
   // trips in which the whole tile is in range need no bounds checks; at most one ragged trip follows
   const uint32_t n_full = rest >= TILE ? (uint32_t)((rest - TILE) / stride) + 1u : 0u;
   const uint32_t n_trips = (uint32_t)((rest + stride - 1) / stride);
@@ -306,7 +325,12 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
 #pragma unroll
     for (int u = 0; u < ROWS_S; ++u) {
       x[u] = param(u, true);
-      ri[u] = rows_span<R, EQUI, POW2, CHECK>(c, rw, x[u], valid[u]);
+      if (HOLD && cached != 0xFFFFFFFFu && x[u] >= row[HOLD_OFF] && x[u] < row[HOLD_OFF + 1]) {
+        ri[u] = cached;  // still inside the cached span: the search would return it again
+        valid[u] = true;
+      } else {
+        ri[u] = rows_span<R, EQUI, POW2, CHECK>(c, rw, x[u], valid[u]);
+      }
     }
     if (!TAKE) tp += stride;
 #pragma unroll
@@ -336,17 +360,23 @@ __host__ __device__ constexpr int rows_min_blocks(int P, int DH) {
 // checks and input adaptors, 2 = take, check-free (the host has proven that no sample of the launch can
 // make the reference panic: t_i = step*fl(i)+start is monotone in i and the set of parameters the
 // reference accepts is an interval unbounded below, so it suffices that both ends of the launch's range
-// are valid). Three kernels rather than three paths in one: the hot loop is I-cache sensitive.
+// are valid), 3 = take, check-free, CHUNKed, rows read from global memory (any table size; sorted knots skip
+// the search while a thread stays in its span). Separate kernels rather than paths in one: the hot loop is
+// I-cache sensitive.
 template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, int VARIANT>
 __global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH)) bspline_rows_kernel(const CurveDev<R> c,
-                                                                                         const SampleSrc<R> s,
-                                                                                         R* __restrict__ out,
-                                                                                         const RowsDev<R> rw) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long mbar;
-  tma_stage(smem_raw, rw.table, rw.bytes, &mbar);
-  const R* __restrict__ tab = reinterpret_cast<const R*>(smem_raw);
-  rows_body<R, DH, PROJ, DEG, EQUI, POW2, VARIANT != 0, VARIANT != 2>(c, s, out, rw, tab);
+                                                                                               const SampleSrc<R> s,
+                                                                                               R* __restrict__ out,
+                                                                                               const RowsDev<R> rw) {
+  if constexpr (VARIANT == 3) {
+    rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, false, true>(c, s, out, rw, rw.table);
+  } else {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar;
+    tma_stage(smem_raw, rw.table, rw.bytes, &mbar);
+    const R* __restrict__ tab = reinterpret_cast<const R*>(smem_raw);
+    rows_body<R, DH, PROJ, DEG, EQUI, POW2, VARIANT != 0, VARIANT != 2, false>(c, s, out, rw, tab);
+  }
 }
 
 }  // namespace enterp

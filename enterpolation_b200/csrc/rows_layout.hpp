@@ -10,6 +10,9 @@ namespace enterp {
 
 constexpr int ROWS_MAX_DEGREE = 7;
 constexpr unsigned ROWS_MAX_BYTES = 64u * 1024u;  // shared-memory budget of the row table per CTA
+// Bigger tables stay in global memory and serve take() only (chunked kernel variant: a CTA walks a contiguous
+// sample range, so a thread's span changes rarely and the row reloads come out of L2).
+constexpr unsigned long long ROWS_GLOBAL_MAX_BYTES = 64ull << 20;
 
 // ---- compile-time schedule of the factor computations ------------------------------------------
 // Factors f(r, j), r = 1..P, j = 0..P-r, use numerator index m = j + r - 1 and denominator
@@ -68,14 +71,20 @@ ENTERP_HD constexpr int sched_find(int P, int W, int r, int j) {
 //   [NOPS*W,     2*NOPS*W)  y = RN(1/den)  (POW2 rows: the exact inverse)
 //   [2*NOPS*W,   3*NOPS*W)  -den
 //   [3*NOPS*W, 3*NOPS*W + (P+1)*DHP)  elements, each padded to DHP = roundup(DH, W) components
+//   [hold_lo, hold_hi) — the parameter interval on which the span computation returns THIS row (-inf / +inf at
+//   the clamped ends), so that a stepper can skip the search / span division while it stays inside
 //   padded to a multiple of 16 bytes.
 template <class R>
 ENTERP_HD constexpr int lanes_of() { return sizeof(R) == 4 ? 2 : 1; }
 ENTERP_HD constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 template <class R>
-ENTERP_HD constexpr int row_len(int P, int DH) {
+ENTERP_HD constexpr int row_hold_off(int P, int DH) {
   const int W = lanes_of<R>();
-  return round_up(3 * sched_nops(P, W) * W + (P + 1) * round_up(DH, W), 16 / (int)sizeof(R));
+  return 3 * sched_nops(P, W) * W + (P + 1) * round_up(DH, W);
+}
+template <class R>
+ENTERP_HD constexpr int row_len(int P, int DH) {
+  return round_up(row_hold_off<R>(P, DH) + 2, 16 / (int)sizeof(R));
 }
 
 

@@ -544,3 +544,38 @@ def test_serde_round_trip_on_device():
         back = serde.loads(kind, serde.dumps(b), "f32")
         assert_bits_equal(back.build().take_device(10007).cpu().numpy(), b.build().take_device(10007).cpu().numpy(), kind)
         assert_bits_equal(back.build().take_device(10007).cpu().numpy(), oracle.OracleCurve(b.to_desc()).take(10007), kind)
+
+
+# ---- chunked global-rows take variant (rows.cuh VARIANT 3) ------------------------------------------------------
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("knots_kind", ["sorted", "sorted_repeats", "equidistant", "equidistant_pow2"])
+@pytest.mark.parametrize("stops,degree,dim,weighted", [(9, 2, 2, 1), (40, 3, 4, 0), (700, 3, 4, 0), (3000, 3, 1, 1), (5000, 5, 3, 0)])
+def test_rows_take_chunked(scalar, knots_kind, stops, degree, dim, weighted):
+    """take() of B-splines through the span-row table in global memory: tables beyond the 64 KB shared-memory
+    budget (equidistant and sorted) and, for sorted knots of any size, the search-skipping hold test. Sample counts
+    put anything from many samples per span to several spans per sample step; windows start mid-take."""
+    dtype = DT[scalar]
+    el = rand_elements(stops, dim, dtype, 0xA1 + stops)
+    b = BSpline.builder().clamped()
+    b = b.elements_with_weights(el, (0.5 + u01(stops, 0xA3, dtype)).astype(dtype)) if weighted else b.elements(el)
+    if knots_kind.startswith("sorted"):
+        k = sorted_knots(stops - degree + 1, dtype, 0xA2, repeat_every=7 if knots_kind == "sorted_repeats" else 0)
+        b = b.knots(k)
+    elif knots_kind == "equidistant":
+        b = b.equidistant(scalar).degree(degree).domain(-1.0, 2.0)
+    else:
+        if (stops - degree) & (stops - degree - 1):
+            pytest.skip("inner knot count - 1 is not a power of two")
+        b = b.equidistant(scalar).degree(degree).normalized()
+    b = b.dynamic()
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    for n in (2, 513, 100003):
+        assert_bits_equal(c.take_device(n).cpu().numpy(), r.take(n), f"take {n}")
+    total = 1 << 22
+    for first, cnt in ((0, 70001), (total // 3, 50000), (total - 1025, 1025)):
+        assert_bits_equal(c.take_device(total, first, cnt).cpu().numpy(), r.take(total, first, cnt), f"window {first}+{cnt}")
+    # batches of the same curves keep their own paths (shared-memory rows when they fit, generic otherwise)
+    d = r.domain()
+    t = (u01(20011, 0xA5, dtype) * dtype(1.2 * float(d[1] - d[0])) + dtype(float(d[0]) - 0.1 * float(d[1] - d[0]))).astype(dtype)
+    assert_bits_equal(c.sample_device(torch.from_numpy(t).cuda()).cpu().numpy(), r.eval(t), "batch")
+    assert_bits_equal(c.clamp().take_device(5000).cpu().numpy(), r.clamp().take(5000), "clamp().take")

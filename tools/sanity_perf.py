@@ -5,15 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from enterpolation_b200 import BSpline, Linear, Bezier, easing
 import bench
 
-def timeit(f, n, label, bytes_per_sample):
-    for _ in range(3): f()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5): f()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    print(f"{label:58s} {n/ms/1e6:8.1f} G samples/s  {n*bytes_per_sample/ms/1e6:7.0f} GB/s")
+from sanity_perf_util import timeit
 
 n = 1 << 28
 el4 = bench.u01(64 * 4, 1, np.float32).reshape(64, 4)
