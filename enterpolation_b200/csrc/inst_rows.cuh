@@ -62,11 +62,11 @@ cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
   // (309 vs 307 G samples/s at 2^32, 261 vs 268 at 2^24) and keep the shared-memory variant.
   if (s.t == nullptr && !need_check && (!EQUI || !POW2 || !fits || rows_force_chunk()))
     return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 3>, c, s, out, rw, 0, st);
-  if (!fits) return cudaErrorNotSupported;  // the caller falls back to the generic kernel
+  if (s.t == nullptr && need_check)  // adaptors / possible panics: same chunked walk with the per-sample checks
+    return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 1>, c, s, out, rw, 0, st);
+  if (!fits) return cudaErrorNotSupported;  // big table and a batch: the caller falls back to the generic kernel
   if (s.t != nullptr)
     return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 0>, c, s, out, rw, rw.bytes, st);
-  if (need_check)
-    return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 1>, c, s, out, rw, rw.bytes, st);
   return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 2>, c, s, out, rw, rw.bytes, st);
 }
 

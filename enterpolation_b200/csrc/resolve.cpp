@@ -357,7 +357,23 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
       tab[(rr - 1) * len + off + 1] = bound;
       tab[rr * len + off] = bound;
     }
-    tab[(n_rows - 1) * len + off + 1] = inf;
+    // The last row ends where the reference starts to panic (floor(scaled).to_usize() fails from 2^64 on,
+    // list.rs:486), so that "inside a hold interval" also means "valid" for the checked kernel variant.
+    auto panics = [&](R x) { return !((x - offset) / step < R(18446744073709551616.0)); };
+    R last_hi = inf;
+    if (panics(FloatKey<R>::value(top))) {
+      I a = from, b = top;
+      if (panics(FloatKey<R>::value(a))) {
+        b = a;
+      } else {
+        while ((uint64_t)b - (uint64_t)a > 1) {
+          const I m = a + (I)(((uint64_t)b - (uint64_t)a) / 2);
+          if (panics(FloatKey<R>::value(m))) b = m; else a = m;
+        }
+      }
+      last_hi = FloatKey<R>::value(b);
+    }
+    tab[(n_rows - 1) * len + off + 1] = last_hi;
   }
   // mode 1 multiplies by exact inverses everywhere (the equidistant span division included), mode 2
   // divides exactly from tabulated reciprocals; both need the span division to be covered.

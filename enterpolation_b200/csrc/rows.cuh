@@ -313,7 +313,14 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
       x = xadd(xmul(s.step, from_index(gi + (unsigned long long)slot * BLOCK, R(0))), s.start);
     else
       x = active ? __ldcs(tp + slot * BLOCK) : c.eq_first;
-    if (CHECK && c.n_pre) x = apply_pre_outlined(c, x);
+    if (CHECK && c.n_pre) {
+      if (c.n_pre == 1) {  // the common single Clamp / affine map inline (uniform branches); chains out of line
+        const R a = c.pre_a[0], b = c.pre_b[0];
+        x = c.pre_kind[0] == 0 ? (x < a ? a : (x > b ? b : x)) : xadd(xmul(x, a), b);
+      } else {
+        x = apply_pre_outlined(c, x);
+      }
+    }
     return x;
   };
 
@@ -357,7 +364,7 @@ __host__ __device__ constexpr int rows_min_blocks(int P, int DH) {
 }
 
 // VARIANT: 0 = batch (parameters read from memory, per-sample panic checks), 1 = take with per-sample
-// checks and input adaptors, 2 = take, check-free (the host has proven that no sample of the launch can
+// checks and input adaptors (CHUNKed, rows from global memory, like 3), 2 = take, check-free (the host has proven that no sample of the launch can
 // make the reference panic: t_i = step*fl(i)+start is monotone in i and the set of parameters the
 // reference accepts is an interval unbounded below, so it suffices that both ends of the launch's range
 // are valid), 3 = take, check-free, CHUNKed, rows read from global memory (any table size; sorted knots skip
@@ -370,6 +377,8 @@ __global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH)) bspline_ro
                                                                                                const RowsDev<R> rw) {
   if constexpr (VARIANT == 3) {
     rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, false, true>(c, s, out, rw, rw.table);
+  } else if constexpr (VARIANT == 1) {
+    rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, true, true>(c, s, out, rw, rw.table);
   } else {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar;

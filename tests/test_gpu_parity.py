@@ -579,3 +579,13 @@ def test_rows_take_chunked(scalar, knots_kind, stops, degree, dim, weighted):
     t = (u01(20011, 0xA5, dtype) * dtype(1.2 * float(d[1] - d[0])) + dtype(float(d[0]) - 0.1 * float(d[1] - d[0]))).astype(dtype)
     assert_bits_equal(c.sample_device(torch.from_numpy(t).cuda()).cpu().numpy(), r.eval(t), "batch")
     assert_bits_equal(c.clamp().take_device(5000).cpu().numpy(), r.clamp().take(5000), "clamp().take")
+    # a slice that runs far out of the domain: decreasing / huge parameters; with equidistant knots the far end
+    # makes the reference panic (floor(scaled) >= 2^64) -> NaN samples and the invalid counter, mid-take
+    for lo_, hi_ in ((float(d[1]), float(d[0])), (float(d[0]), 1e30)):
+        cs, rs = c.slice(lo_, hi_), r.slice(lo_, hi_)
+        before = c.invalid_count()
+        got = cs.take_device(40001).cpu().numpy()
+        want, inv = rs.take(40001, return_invalid=True)
+        assert_bits_equal(got, want, f"slice({lo_}, {hi_}).take")
+        assert c.invalid_count() - before == inv
+        assert (inv > 0) == (hi_ == 1e30 and knots_kind.startswith("equidistant"))

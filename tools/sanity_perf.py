@@ -31,7 +31,7 @@ c = BSpline.builder().clamped().elements(el4[:9]).equidistant("f32").degree(3).n
 t = torch.rand(n, device="cuda", dtype=torch.float32)
 timeit(lambda: c.sample_device(t, out=out4), n, "cubic equidistant [f32;4] random batch (rows)", 20)
 cc = c.clamp()
-timeit(lambda: cc.take_device(n, out=out4), n, "same curve .clamp() take (generic kernel)", 16)
+timeit(lambda: cc.take_device(n, out=out4), n, "same curve .clamp() take (checked rows variant)", 16)
 c = BSpline.builder().clamped().elements(bench.u01(12, 2, np.float32)).equidistant("f32").degree(5).normalized().dynamic().build()
 out1 = torch.empty(n, dtype=torch.float32, device="cuda")
 timeit(lambda: c.take_device(n, out=out1), n, "quintic equidistant f32 scalar take (rows)", 4)
