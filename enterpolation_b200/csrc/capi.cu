@@ -343,7 +343,7 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
       break;
     }
     case ENTERP_LINEAR:
-      if (equi && !g_disable_lean && lean_linear<R>(r.dh, proj, d, s, static_cast<R*>(out), vec_ok, st, &e)) break;
+      if (!g_disable_lean && lean_linear<R>(r.dh, proj, equi, d, s, static_cast<R*>(out), vec_ok, st, &e)) break;
       e = launch_linear<R>(r.dh, proj, equi, d, s, static_cast<R*>(out), vec_ok, st);
       break;
     default: {

@@ -45,12 +45,52 @@ cudaError_t lean_linear_pick(int mode, const LeanLinear<R>& c, const LeanTake<R>
   return lean_linear_pick_mode<R, DH, PROJ, false, BATCH>(mode, c, t, ts, out, st);
 }
 
+template <class R, int DH, bool PROJ>
+cudaError_t lean_linear_sorted_pick(const CurveDev<R>& c, const LeanLinear<R>& l, const LeanTake<R>& t, R* out,
+                                    cudaStream_t st) {
+  if (l.easing) return launch_grid_stride(linear_sorted_take_kernel<R, DH, PROJ, true>, t.count, BLOCK, st, c, l, t, out);
+  return launch_grid_stride(linear_sorted_take_kernel<R, DH, PROJ, false>, t.count, BLOCK, st, c, l, t, out);
+}
+
+// take() over sorted knots: needs the interval-record table (resolve.hpp) and nothing else
+template <class R>
+bool lean_linear_sorted_take(int dh, bool proj, const CurveDev<R>& c, const LeanTake<R>& t, R* out, cudaStream_t st,
+                             cudaError_t* err) {
+  if (c.records == nullptr || c.rec_stride != (uint32_t)linear_rec_stride<R>(dh)) return false;
+  LeanLinear<R> l{};
+  l.easing = c.easing;
+  l.easing_n = c.easing_n;
+  l.ease_min = c.ease_min;
+  l.ease_max = c.ease_max;
+  *err = cudaErrorInvalidValue;
+  if (!proj) {
+    switch (dh) {
+      case 1: *err = lean_linear_sorted_pick<R, 1, false>(c, l, t, out, st); break;
+      case 2: *err = lean_linear_sorted_pick<R, 2, false>(c, l, t, out, st); break;
+      case 3: *err = lean_linear_sorted_pick<R, 3, false>(c, l, t, out, st); break;
+      case 4: *err = lean_linear_sorted_pick<R, 4, false>(c, l, t, out, st); break;
+    }
+  } else {
+    switch (dh) {
+      case 2: *err = lean_linear_sorted_pick<R, 2, true>(c, l, t, out, st); break;
+      case 3: *err = lean_linear_sorted_pick<R, 3, true>(c, l, t, out, st); break;
+      case 4: *err = lean_linear_sorted_pick<R, 4, true>(c, l, t, out, st); break;
+      case 5: *err = lean_linear_sorted_pick<R, 5, true>(c, l, t, out, st); break;
+    }
+  }
+  return true;
+}
+
 template <class R, bool BATCH>
-bool lean_linear_impl(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
+bool lean_linear_impl(int dh, bool proj, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
                       cudaStream_t st, cudaError_t* err) {
   LeanTake<R> t{};
   if (!lean_src<R, BATCH>(s, vec_ok, t)) return false;
   if (c.n_pre != 0 || c.inner_len < 2 || c.inner_len > 0x7fffffffu) return false;
+  if (!equi) {
+    if constexpr (BATCH) return false;  // random parameters over sorted knots: the generic kernel (staged pivot levels)
+    else return lean_linear_sorted_take<R>(dh, proj, c, t, out, st, err);
+  }
   const int mode = c.eq_const ? 0 : (c.eq_mode == 1 ? 1 : (c.eq_mode == 2 ? 2 : 3));
   if (!BATCH) {
     if (!(c.eq_step > R(0)) || !(t.step >= R(0))) return false;  // also rejects NaN
@@ -150,9 +190,9 @@ bool lean_bezier_impl(int dh, bool proj, int n, const R* host_elems, const Curve
 #define ENTERP_DEFINE_LEAN(R, BATCH)                                                                                   \
   namespace enterp {                                                                                                   \
   template <>                                                                                                          \
-  bool lean_linear_part<R, BATCH>(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok, \
-                                  cudaStream_t st, cudaError_t* err) {                                                 \
-    return lean_linear_impl<R, BATCH>(dh, proj, c, s, out, vec_ok, st, err);                                           \
+  bool lean_linear_part<R, BATCH>(int dh, bool proj, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,   \
+                                  bool vec_ok, cudaStream_t st, cudaError_t* err) {                                    \
+    return lean_linear_impl<R, BATCH>(dh, proj, equi, c, s, out, vec_ok, st, err);                                     \
   }                                                                                                                    \
   template <>                                                                                                          \
   bool lean_bezier_part<R, BATCH>(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c,                 \

@@ -60,16 +60,16 @@ cudaError_t launch_bezier(int dh, bool proj, int n, const CurveDev<R>& c, const 
 // Lean kernels (lean.cuh): launch and return true when the call qualifies (status in *err), else false.
 // host_elems: the curve's lifted control values on the host ([n][dh]). One translation unit per (R, BATCH).
 template <class R, bool BATCH>
-bool lean_linear_part(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok, cudaStream_t st,
-                      cudaError_t* err);
+bool lean_linear_part(int dh, bool proj, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
+                      cudaStream_t st, cudaError_t* err);
 template <class R, bool BATCH>
 bool lean_bezier_part(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
                       bool vec_ok, cudaStream_t st, cudaError_t* err);
 template <class R>
-inline bool lean_linear(int dh, bool proj, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok, cudaStream_t st,
-                        cudaError_t* err) {
-  return s.t ? lean_linear_part<R, true>(dh, proj, c, s, out, vec_ok, st, err)
-             : lean_linear_part<R, false>(dh, proj, c, s, out, vec_ok, st, err);
+inline bool lean_linear(int dh, bool proj, bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
+                        cudaStream_t st, cudaError_t* err) {
+  return s.t ? lean_linear_part<R, true>(dh, proj, equi, c, s, out, vec_ok, st, err)
+             : lean_linear_part<R, false>(dh, proj, equi, c, s, out, vec_ok, st, err);
 }
 template <class R>
 inline bool lean_bezier(int dh, bool proj, int n, const R* host_elems, const CurveDev<R>& c, const SampleSrc<R>& s, R* out,

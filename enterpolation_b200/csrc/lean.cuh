@@ -141,6 +141,54 @@ __global__ void __launch_bounds__(BLOCK) linear_equi_lean_kernel(const LeanLinea
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Linear over sorted knots, take(): every CTA walks one contiguous range of samples, so a thread's parameter moves
+// by BLOCK stepper steps per trip and usually stays inside the knot interval whose record (both knots, both
+// elements; resolve.hpp) it already holds in registers: the pivot search (list.rs:69-86, 169-203) and the record
+// load run only when k_j <= x < k_{j+1} fails. That test is exactly the interior case of upper_border (m - 1 == j),
+// so the edge rules (left of / at or right of all knots, NaN) are always decided by the search itself.
+// ---------------------------------------------------------------------------------------------------------------
+// (BLOCK, 4): without a min-blocks hint ptxas settles on 32 registers and spills the tile counter into the loop
+template <class R, int DH, bool PROJ, bool EASE>
+__global__ void __launch_bounds__(BLOCK, 4) linear_sorted_take_kernel(const CurveDev<R> c, const LeanLinear<R> l,
+                                                                   const LeanTake<R> s, R* __restrict__ out) {
+  constexpr int STRIDE = linear_rec_stride<R>(DH);
+  const uint32_t tiles = (s.count + BLOCK - 1) / BLOCK;
+  const uint32_t per = (tiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t t0 = blockIdx.x * per;
+  const uint32_t t1 = min(tiles, t0 + per);
+  R rec[STRIDE];
+  R div = R(0);
+  bool have = false;
+  for (uint32_t tile = t0; tile < t1; ++tile) {
+    const uint32_t i = tile * BLOCK + threadIdx.x;
+    if (i >= s.count) break;  // ragged last tile of the launch
+    const R x = xadd(xmul(s.step, from_u32(s.first + i, R(0))), s.start);
+    bool edge = false;
+    if (!(have && x >= rec[0] && x < rec[1])) {
+      const uint32_t len = c.inner_len;
+      const uint32_t m = count_le(c, x);
+      edge = (m == len) || (m == 0);
+      const uint32_t imax = m == len ? len - 1 : (m == 0 ? 1u : m);
+      load_vec<STRIDE, (STRIDE * (int)sizeof(R)) % 32 == 0>(c.records + (size_t)(imax - 1u) * STRIDE, rec);
+      div = xsub(rec[1], rec[0]);
+      have = true;
+    }
+    // linear_factor (checked, list.rs:232-248) on the edges, linear_factor_unchecked (212-224) inside
+    R f = (edge && div == R(0)) ? div : xdiv(xsub(x, rec[0]), div);
+    if constexpr (EASE) f = lean_easing(l, f);
+    const R omf = xsub(R(1), f);
+    R w[DH];
+#pragma unroll
+    for (int k = 0; k < DH; ++k) w[k] = merge1(rec[2 + k], rec[2 + DH + k], f, omf);
+    constexpr int D = PROJ ? DH - 1 : DH;
+    R v[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = PROJ ? xdiv(w[k], w[DH - 1]) : w[k];
+    store_elem<R, D>(out, i, v, true);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Bezier: the control values travel in the kernel parameter block (constant bank), so the first de Casteljau
 // level reads them as instruction operands and no load is issued per sample.
 // ---------------------------------------------------------------------------------------------------------------

@@ -589,3 +589,32 @@ def test_rows_take_chunked(scalar, knots_kind, stops, degree, dim, weighted):
         assert_bits_equal(got, want, f"slice({lo_}, {hi_}).take")
         assert c.invalid_count() - before == inv
         assert (inv > 0) == (hi_ == 1e30 and knots_kind.startswith("equidistant"))
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("dim,weighted", [(1, 0), (2, 0), (3, 0), (4, 0), (1, 1), (3, 1), (4, 1)])
+@pytest.mark.parametrize("n_knots,repeats", [(2, 0), (3, 0), (37, 0), (37, 5), (5000, 0), (5000, 3)])
+def test_lean_linear_sorted_take(scalar, dim, weighted, n_knots, repeats):
+    """take() of Linear over sorted knots (chunked walk, the search is skipped inside the held knot interval):
+    few and many samples per interval, repeated knots incl. coincident edge knots, easings, windows."""
+    dtype = DT[scalar]
+    el = rand_elements(n_knots, dim, dtype, 0xB1 + n_knots)
+    knots = sorted_knots(n_knots, dtype, 0xB2, repeat_every=repeats)
+    if repeats and n_knots > 4:
+        knots[1] = knots[0]
+        knots[-2] = knots[-1]
+    b = Linear.builder()
+    b = b.elements_with_weights(el, (0.5 + u01(n_knots, 0xB3, dtype)).astype(dtype)) if weighted else b.elements(el)
+    b = b.knots(knots)
+    if (dim + weighted) % 2 == 0:
+        from enterpolation_b200 import easing as E
+        b = b.easing([E.smoothstep, E.Plateau(0.4), E.smoothstart(3), E.flip][dim - 1])
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    for n in (2, 3, 255, 257, 100003):
+        assert_bits_equal(c.take_device(n).cpu().numpy(), r.take(n), f"take {n}")
+    total = 1 << 22
+    for first, cnt in ((0, 70001), (total // 3, 50000), (total - 1025, 1025)):
+        assert_bits_equal(c.take_device(total, first, cnt).cpu().numpy(), r.take(total, first, cnt), f"window {first}+{cnt}")
+    n_total = (1 << 32) + 12345
+    for first in ((1 << 32) - (1 << 24) - 3000, (1 << 32) - 1500):
+        assert_bits_equal(c.take_device(n_total, first, 3000).cpu().numpy(), r.take(n_total, first, 3000), f"first={first}")

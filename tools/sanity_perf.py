@@ -14,6 +14,12 @@ c = Linear.builder().elements(el4).equidistant("f32").normalized().build()
 timeit(lambda: c.take_device(n, out=out4), n, "Linear equidistant [f32;4] take", 16)
 c = Linear.builder().elements(el4).equidistant("f32").normalized().easing(easing.smoothstep).build()
 timeit(lambda: c.take_device(n, out=out4), n, "Linear equidistant [f32;4] smoothstep take", 16)
+kn = np.cumsum(0.5 + bench.u01(64, 3, np.float64)).astype(np.float32)
+c = Linear.builder().elements(el4).knots(kn).build()
+timeit(lambda: c.take_device(n, out=out4), n, "Linear sorted knots (64) [f32;4] take", 16)
+kn = np.cumsum(0.5 + bench.u01(1 << 16, 3, np.float64)).astype(np.float32)
+c = Linear.builder().elements(bench.u01(4 << 16, 1, np.float32).reshape(-1, 4)).knots(kn).build()
+timeit(lambda: c.take_device(n, out=out4), n, "Linear sorted knots (65536) [f32;4] take", 16)
 tb = torch.rand(n, device="cuda", dtype=torch.float32)
 c = Linear.builder().elements(el4).equidistant("f32").normalized().build()
 timeit(lambda: c.sample_device(tb, out=out4), n, "Linear equidistant [f32;4] random batch", 20)
