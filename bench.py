@@ -602,7 +602,11 @@ def run_gpu(args):
                                            "launch x this launch's samples)",
                          "kernel": rows_kernel,
                          "algorithmic_bytes_per_sample": 16, "peak_source": f"MEASURED_PEAKS.json ({how}, burst copy)",
-                         "fp32_pipe_frac": c5_samples * 125 / (per_launch_ms * 1e-3) / FP32_LANE_OPS},
+                         # FMA-pipe lane-operations the kernel has to execute per sample: 72 (six unfused merges of four
+                         # components) + 12 (six factors: subtract, multiply by the exact inverse) + 6 (1 - f) + 3 (stepper,
+                         # span) = 93; the reference's own order has 125 (it regenerates knots and divides), DESIGN.md §4
+                         "fp32_pipe_frac": c5_samples * 93 / (per_launch_ms * 1e-3) / FP32_LANE_OPS,
+                         "fp32_lane_ops_per_sample": 93, "reference_order_fp_ops_per_sample": 125},
             "cpu_baseline": {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
                              "single_thread": cpu_1t,
                              "sample": f"{1 << 25} consecutive samples (all cores) / {1 << 22} (1 thread) from the middle of the take; "
