@@ -52,6 +52,12 @@ static const bool g_no_records = [] {
   return v && v[0] == '1';
 }();
 
+// Ablation switch (env ENTERP_NO_BUCKETS=1): sorted searches descend the pivot tree only.
+static const bool g_no_buckets = [] {
+  const char* v = std::getenv("ENTERP_NO_BUCKETS");
+  return v && v[0] == '1';
+}();
+
 // Ablation switch (env ENTERP_NO_SMEM_PIVOTS=1): leave every pivot level in global memory / L1.
 static const bool g_no_smem_pivots = [] {
   const char* v = std::getenv("ENTERP_NO_SMEM_PIVOTS");
@@ -106,6 +112,7 @@ struct Replica {
   void* records = nullptr;
   void* knot_rows = nullptr;
   void* pyramid = nullptr;              // all pivot levels, top first, one allocation
+  void* buckets = nullptr;              // bucket index of the sorted search (resolve.hpp)
   uint32_t lvl_off[MAX_LEVELS] = {};    // element offsets of the levels inside it
   uint32_t lvl_last[MAX_LEVELS] = {};   // last node index of each level
   int n_lvl = 0;
@@ -142,6 +149,7 @@ struct CurveCore {
       cudaFree(rp->records);
       cudaFree(rp->knot_rows);
       cudaFree(rp->pyramid);
+      cudaFree(rp->buckets);
       cudaFree(rp->invalid);
       delete rp;
     }
@@ -210,6 +218,14 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
       rp->n_top = n_top;
     }
   }
+  if (e == cudaSuccess && !c->core->r.buckets.empty() && !g_no_buckets) {
+    const std::vector<uint32_t>& b = c->core->r.buckets;
+    e = cudaMalloc(&rp->buckets, b.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(rp->buckets, b.data(), b.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    // with the bucket index the tree is only a fallback for crowded buckets: do not spend shared memory on it
+    rp->top_bytes = 0;
+    rp->n_top = 0;
+  }
   if (e == cudaSuccess) e = cudaMalloc((void**)&rp->invalid, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(rp->invalid, 0, sizeof(unsigned long long));
   if (e != cudaSuccess) {
@@ -219,6 +235,7 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
     cudaFree(rp->records);
     cudaFree(rp->knot_rows);
     cudaFree(rp->pyramid);
+    cudaFree(rp->buckets);
     cudaFree(rp->invalid);
     delete rp;
     return cuda_fail(e, "curve upload");
@@ -253,6 +270,10 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   }
   d.n_top = rp.n_top;
   d.top_bytes = rp.top_bytes;
+  d.bkt = static_cast<const uint32_t*>(rp.buckets);
+  d.n_bkt = rp.buckets ? (uint32_t)(r.buckets.size() - 1) : 0;
+  d.bkt_first = (R)r.bkt_first;
+  d.bkt_inv = (R)r.bkt_inv;
   d.n_elem = (uint32_t)r.n_elem;
   d.inner_len = (uint32_t)r.inner_len;
   d.virt_len = (uint32_t)r.virt_len;

@@ -34,6 +34,10 @@ struct CurveDev {
   int n_lvl;
   int n_top;           // levels [0, n_top) are staged into shared memory by the kernel (0: none)
   uint32_t top_bytes;  // their total size (multiple of 32)
+  // Bucket index of the searched knot range (resolve.hpp), or nullptr: prefix counts [n_bkt + 1]
+  const uint32_t* bkt;
+  uint32_t n_bkt;
+  R bkt_first, bkt_inv;
   uint32_t n_elem, inner_len, virt_len, degree;
   uint32_t imin, imax, map0, mapL;
   int32_t map_add;
@@ -287,8 +291,41 @@ struct Node<double> {
 };
 
 // `top`: shared-memory copy of levels [0, n_top) (nullptr when nothing is staged).
+__device__ __forceinline__ uint32_t bucket_sat_u32(float v) { return __float2uint_rz(v); }   // saturating above 2^32
+__device__ __forceinline__ uint32_t bucket_sat_u32(double v) { return __double2uint_rz(v); }
+constexpr uint32_t BUCKET_SCAN = 4;  // knots compared inside one bucket before falling back to the tree (resolve.cpp)
+
+// Pivot-tree descent (below). `top`: shared-memory copy of levels [0, n_top) (nullptr when nothing is staged).
+template <class R>
+__device__ __forceinline__ uint32_t count_le_tree(const CurveDev<R>& c, R x, const R* __restrict__ top);
+
+// Big sorted knot vectors: the bucket index turns the descent into two dependent loads. bucket(x) is monotone, so
+// every knot of a lower bucket is < x and every knot of a higher bucket is > x; only the knots sharing x's bucket
+// (usually none or one) are compared. NaN lands in bucket 0 and compares false everywhere (count 0, as the
+// reference's search returns its lower bound for NaN).
 template <class R>
 __device__ __forceinline__ uint32_t count_le(const CurveDev<R>& c, R x, const R* __restrict__ top = nullptr) {
+  uint32_t lo = 0, hi = 0;
+  bool tree = c.bkt == nullptr;
+  if (!tree) {
+    const R tq = xmul(xsub(x, c.bkt_first), c.bkt_inv);
+    // NaN must land in bucket 0 explicitly: the f64 -> u32 conversion does not map NaN to 0 (measured on sm_100a)
+    const uint32_t b = min(tq >= R(0) ? bucket_sat_u32(tq) : 0u, c.n_bkt - 1u);
+    lo = __ldg(c.bkt + b);
+    hi = __ldg(c.bkt + b + 1u);
+    tree = hi - lo > BUCKET_SCAN;
+  }
+  if (tree) return count_le_tree(c, x, top);  // one call site: the unrolled descent is big
+  const R* __restrict__ k = c.ik + c.imin + lo;
+  uint32_t cnt = lo;
+#pragma unroll
+  for (uint32_t q = 0; q < BUCKET_SCAN; ++q)
+    if (lo + q < hi) cnt += (__ldg(k + q) <= x) ? 1u : 0u;
+  return cnt;
+}
+
+template <class R>
+__device__ __forceinline__ uint32_t count_le_tree(const CurveDev<R>& c, R x, const R* __restrict__ top) {
   constexpr uint32_t FAN = Node<R>::FAN;
   uint32_t cnt = 0;
 #pragma unroll

@@ -22,7 +22,7 @@ namespace enterp {
 
 __device__ __forceinline__ float from_u32(uint32_t i, float) { return __uint2float_rn(i); }
 __device__ __forceinline__ double from_u32(uint32_t i, double) { return __uint2double_rn(i); }
-// saturating conversions (negative / NaN -> 0): defined for every input, unlike the C++ cast
+// saturating conversions (negative -> 0, huge -> 2^32 - 1); NaN results are overridden by the callers
 __device__ __forceinline__ uint32_t to_u32(float v) { return __float2uint_rz(v); }
 __device__ __forceinline__ uint32_t to_u32(double v) { return __double2uint_rz(v); }
 

@@ -390,6 +390,51 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
   std::memcpy(r.rows.data(), tab.data(), r.rows.size());
 }
 
+// Bucket index of the sorted search (resolve.hpp). Worth it for big knot vectors only (small ones live in L1 /
+// shared memory anyway) and only when the knots spread over the buckets: the kernel compares at most
+// BUCKET_SCAN knots of a bucket and falls back to the pivot tree beyond that.
+constexpr uint32_t BUCKET_SCAN = 4;
+template <class R>
+uint32_t bucket_of(R x, R first, R inv, uint32_t n_buckets) {
+  const R t = (x - first) * inv;  // same two IEEE operations as the kernel (count_le, kernels.cuh)
+  const uint32_t b = !(t >= R(0)) ? 0u : (t >= R(4294967295.0) ? 0xFFFFFFFFu : (uint32_t)t);
+  return b < n_buckets - 1u ? b : n_buckets - 1u;
+}
+template <class R>
+void build_buckets(Resolved& r, const R* knots, uint64_t n) {
+  r.buckets.clear();
+  if (n < 4096 || n > (1ull << 30)) return;
+  const R first = knots[0], last = knots[n - 1];
+  if (!(last > first) || !std::isfinite(first) || !std::isfinite(last)) return;
+  uint64_t nb = 1;
+  while (nb < 2 * n) nb <<= 1;
+  if (nb > (1ull << 24)) nb = 1ull << 24;
+  const R width = last - first;
+  const R inv = (R)nb / width;
+  if (!std::isfinite(width) || !std::isfinite(inv) || !(inv > R(0))) return;
+  std::vector<uint32_t> tab(nb + 1, 0);
+  uint64_t crowded = 0;  // knots living in buckets the kernel would not scan
+  uint32_t prev = 0;
+  std::vector<uint32_t> cnt(nb, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t b = bucket_of<R>(knots[i], first, inv, (uint32_t)nb);
+    if (b < prev) return;  // cannot happen for sorted knots (bucket_of is monotone); be safe
+    prev = b;
+    ++cnt[b];
+  }
+  uint32_t run = 0;
+  for (uint64_t b = 0; b < nb; ++b) {
+    tab[b] = run;
+    run += cnt[b];
+    if (cnt[b] > BUCKET_SCAN) crowded += cnt[b];
+  }
+  tab[nb] = run;
+  if (crowded * 50 > n) return;  // more than 2 % of the knots are clustered: keep the pivot tree alone
+  r.buckets = std::move(tab);
+  r.bkt_first = first;
+  r.bkt_inv = inv;
+}
+
 template <class R>
 void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
   const R nan = std::numeric_limits<R>::quiet_NaN();
@@ -552,6 +597,7 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
       r.levels.level.push_back(std::move(raw));
     }
   }
+  if (d.knot_base == ENTERP_KNOTS_SORTED) build_buckets<R>(r, inner.data() + r.imin, r.imax - r.imin);
 
   // How the kernels may compute (x - offset) / step exactly without the IEEE divide (rows.cuh header):
   // 1 = step is a power of two (multiply by the exact inverse), 2 = exact division from RN(1/step).

@@ -47,6 +47,12 @@ struct Resolved {
   // elements, lifted to homogeneous form when weighted: [n_elem][dh]
   std::vector<unsigned char> elems;
   SearchLevels levels;
+  // Bucket index over the searched knot range (sorted knots): B equal-width buckets of [first, last];
+  // buckets[b] = number of searched knots whose bucket is < b (B + 1 prefix counts). bucket(x) is the monotone
+  // function clamp(trunc((x - first) * inv), 0, B - 1) evaluated in R, so the knots <= x are those of the lower
+  // buckets plus a compare over the few knots sharing x's bucket. Empty when the knots are too clustered for it.
+  std::vector<uint32_t> buckets;
+  double bkt_first = 0, bkt_inv = 0;
   double domain[2] = {0, 0};
   // Bezier TransformInput (base/adaptors.rs:137-139)
   int32_t has_transform = 0;

@@ -120,7 +120,7 @@ __device__ __forceinline__ typename PK<R>::T exact_div(typename PK<R>::T num, ty
 template <class R>
 __device__ __forceinline__ uint32_t sat_u32(R v);
 template <>
-__device__ __forceinline__ uint32_t sat_u32<float>(float v) { return __float2uint_rz(v); }   // saturating, NaN -> 0
+__device__ __forceinline__ uint32_t sat_u32<float>(float v) { return __float2uint_rz(v); }   // saturating; NaN is never relied on
 template <>
 __device__ __forceinline__ uint32_t sat_u32<double>(double v) { return __double2uint_rz(v); }
 

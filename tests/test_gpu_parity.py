@@ -618,3 +618,31 @@ def test_lean_linear_sorted_take(scalar, dim, weighted, n_knots, repeats):
     n_total = (1 << 32) + 12345
     for first in ((1 << 32) - (1 << 24) - 3000, (1 << 32) - 1500):
         assert_bits_equal(c.take_device(n_total, first, 3000).cpu().numpy(), r.take(n_total, first, 3000), f"first={first}")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("shape", ["uniform", "one_cluster", "heavy_clusters", "repeats", "huge_range", "tiny_range"])
+def test_bucket_index_search(scalar, shape):
+    """Sorted searches over >= 4096 knots go through the bucket index (kernels.cuh count_le): spread-out knots, a
+    cluster that overflows its bucket (tree fallback at run time), clustering that disables the index at build time,
+    repeated knots, extreme knot ranges. Parameters: every knot, its float neighbours, out-of-domain, NaN, inf."""
+    dtype = DT[scalar]
+    rng = np.random.default_rng(11)
+    n = 8192
+    k = np.cumsum(0.5 + u01(n, 0xD2, np.float64))
+    if shape == "one_cluster":
+        k[3000:3100] = k[3000] + np.arange(100) * 1e-3
+    elif shape == "heavy_clusters":
+        k = np.sort(np.concatenate([k[: n // 2], k[n // 2] + u01(n // 2, 0xD3, np.float64) * 1e-2]))
+    elif shape == "repeats":
+        k[1::3] = k[0::3][: len(k[1::3])]
+        k = np.sort(k)
+    elif shape == "huge_range":
+        k = k * (1e30 if scalar == "f32" else 1e250)
+    elif shape == "tiny_range":
+        k = 1.0 + k * (2e-7 if scalar == "f32" else 3e-16)
+    k = np.sort(k.astype(dtype))
+    t = adversarial(k, dtype, rng, n_random=20000)
+    t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+    check_curve(Linear.builder().elements(rand_elements(n, 3, dtype, 0xD4)).knots(k), t, what=f"linear {shape}")
+    check_curve(BSpline.builder().elements(rand_elements(n - 2, 2, dtype, 0xD5)).knots(k).constant(4), t, what=f"bspline {shape}")
