@@ -412,7 +412,7 @@ void build_buckets(Resolved& r, const R* knots, uint64_t n) {
   const R width = last - first;
   const R inv = (R)nb / width;
   if (!std::isfinite(width) || !std::isfinite(inv) || !(inv > R(0))) return;
-  std::vector<uint32_t> tab(nb + 1, 0);
+  std::vector<uint32_t> tab(2 * nb, 0);  // pairs {prefix count, knots in the bucket}: one 8-byte load per lookup
   uint64_t crowded = 0;  // knots living in buckets the kernel would not scan
   uint32_t prev = 0;
   std::vector<uint32_t> cnt(nb, 0);
@@ -424,11 +424,11 @@ void build_buckets(Resolved& r, const R* knots, uint64_t n) {
   }
   uint32_t run = 0;
   for (uint64_t b = 0; b < nb; ++b) {
-    tab[b] = run;
+    tab[2 * b] = run;
+    tab[2 * b + 1] = cnt[b];
     run += cnt[b];
     if (cnt[b] > BUCKET_SCAN) crowded += cnt[b];
   }
-  tab[nb] = run;
   if (crowded * 50 > n) return;  // more than 2 % of the knots are clustered: keep the pivot tree alone
   r.buckets = std::move(tab);
   r.bkt_first = first;
