@@ -156,10 +156,39 @@ __device__ __forceinline__ uint32_t rows_span(const CurveDev<R>& c, const RowsDe
   return min(inner + rw.ri_off, rw.n_rows - 1u);  // the clamp is a no-op for every valid sample
 }
 
-// Out of line on purpose: the hot kernel must stay small (its adaptor-free loops are I-cache sensitive).
+// Chains of input adaptors run out of line on purpose: the hot kernel must stay small (its adaptor-free loops are
+// I-cache sensitive). The list travels BY VALUE: a reference to the kernel's CurveDev parameter would make the
+// compiler copy the whole ~470-byte struct into every thread's local memory to have an address for it.
 template <class R>
-__device__ __noinline__ R apply_pre_outlined(const CurveDev<R>& c, R x) {
-  return apply_pre(c, x);
+struct PreList {
+  int n;
+  int kind[MAX_PRE];
+  R a[MAX_PRE], b[MAX_PRE];
+};
+template <class R>
+__device__ __noinline__ R apply_pre_list(const PreList<R> p, R x) {
+#pragma unroll
+  for (int i = 0; i < MAX_PRE; ++i) {
+    if (i < p.n) {
+      if (p.kind[i] == 0)
+        x = x < p.a[i] ? p.a[i] : (x > p.b[i] ? p.b[i] : x);  // Clamp::eval, adaptors.rs:26-32
+      else
+        x = xadd(xmul(x, p.a[i]), p.b[i]);                     // TransformInput::eval, adaptors.rs:141-152
+    }
+  }
+  return x;
+}
+template <class R>
+__device__ __forceinline__ R apply_pre_outlined(const CurveDev<R>& c, R x) {
+  PreList<R> p;
+  p.n = c.n_pre;
+#pragma unroll
+  for (int i = 0; i < MAX_PRE; ++i) {
+    p.kind[i] = c.pre_kind[i];
+    p.a[i] = c.pre_a[i];
+    p.b[i] = c.pre_b[i];
+  }
+  return apply_pre_list<R>(p, x);
 }
 
 constexpr int ROWS_S = 2;  // samples per thread per loop trip (block-strided, so stores stay coalesced)
@@ -307,6 +336,17 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
 
   // Input adaptors (Clamp / Slice / Bezier-style affine maps, base/adaptors.rs) ride on the CHECK variant
   // only, so the adaptor-free take loop stays as lean as it is.
+  auto pre_only = [&](R x) -> R {
+    if (CHECK && c.n_pre) {
+      if (c.n_pre == 1) {
+        const R a = c.pre_a[0], b = c.pre_b[0];
+        x = c.pre_kind[0] == 0 ? (x < a ? a : (x > b ? b : x)) : xadd(xmul(x, a), b);
+      } else {
+        x = apply_pre_outlined(c, x);
+      }
+    }
+    return x;
+  };
   auto param = [&](const int slot, const bool active) -> R {
     R x;
     if (TAKE)
@@ -324,14 +364,30 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
     return x;
   };
 
+  // Batches: the parameters of the NEXT trip are requested before this trip's arithmetic, so their DRAM latency
+  // hides behind ~130 instructions of de Boor instead of stalling the head of every trip.
+  R ahead[ROWS_S];
+  if (!TAKE && n_full > 0) {
+#pragma unroll
+    for (int u = 0; u < ROWS_S; ++u) ahead[u] = __ldcs(tp + u * BLOCK);
+  }
+
   uint32_t k = 0;
   for (; k < n_full; ++k, gi += stride, op += stride * D) {
     R x[ROWS_S];
     bool valid[ROWS_S];
     uint32_t ri[ROWS_S];
+    if (!TAKE) {
+#pragma unroll
+      for (int u = 0; u < ROWS_S; ++u) x[u] = ahead[u];
+      if (k + 1 < n_full) {
+#pragma unroll
+        for (int u = 0; u < ROWS_S; ++u) ahead[u] = __ldcs(tp + stride + u * BLOCK);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < ROWS_S; ++u) {
-      x[u] = param(u, true);
+      x[u] = TAKE ? param(u, true) : pre_only(x[u]);
       if (HOLD && cached != 0xFFFFFFFFu && x[u] >= row[HOLD_OFF] && x[u] < row[HOLD_OFF + 1]) {
         ri[u] = cached;  // still inside the cached span: the search would return it again
         valid[u] = true;
