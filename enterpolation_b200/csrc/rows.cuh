@@ -415,8 +415,9 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
 // Occupancy hint: small rows (cubic [f32;4] needs 36 row registers) fit 4 CTAs/SM under a 64-register
 // cap; bigger rows keep the default so that they do not spill.
 template <class R>
-__host__ __device__ constexpr int rows_min_blocks(int P, int DH) {
-  return row_len<R>(P, DH) * (int)(sizeof(R) / 4) <= 40 ? 4 : 1;
+__host__ __device__ constexpr int rows_min_blocks(int P, int DH, bool POW2) {
+  // exact-division rows keep y and -den of every factor live as well: 3 CTAs/SM (85 registers) instead of spilling
+  return row_len<R>(P, DH) * (int)(sizeof(R) / 4) <= 40 ? (POW2 ? 4 : 3) : 1;
 }
 
 // VARIANT: 0 = batch (parameters read from memory, per-sample panic checks), 1 = take with per-sample
@@ -427,7 +428,7 @@ __host__ __device__ constexpr int rows_min_blocks(int P, int DH) {
 // the search while a thread stays in its span). Separate kernels rather than paths in one: the hot loop is
 // I-cache sensitive.
 template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, int VARIANT>
-__global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH)) bspline_rows_kernel(const CurveDev<R> c,
+__global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH, POW2)) bspline_rows_kernel(const CurveDev<R> c,
                                                                                                const SampleSrc<R> s,
                                                                                                R* __restrict__ out,
                                                                                                const RowsDev<R> rw) {
