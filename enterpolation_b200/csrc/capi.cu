@@ -355,6 +355,7 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
         rw.one = R(1);
         rw.eq_rstep = (R)r.eq_rstep;
         rw.ri_off = (uint32_t)((int64_t)r.map_add - (int64_t)r.rows_lo);
+        rw.pow2_ops = r.rows_pow2_ops;
         e = launch_bspline_rows<R>(r.dh, proj, deg, equi, r.rows_mode == 1, d, s, static_cast<R*>(out), rw, st);
         if (e == cudaErrorNotSupported)  // table too big for shared memory and not a plain take(): generic kernel
           e = launch_bspline<R>(r.dh, proj, deg, equi, d, s, static_cast<R*>(out), vec_ok, st);

@@ -283,6 +283,7 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
   std::vector<R> tab((size_t)n_rows * len, R(0));
   const R* el = reinterpret_cast<const R*>(r.elems.data());
   bool all_pow2 = true, all_window = true;
+  uint32_t op_pow2 = (1u << nops) - 1u;  // bit t: every needed row has power-of-two denominators in all lanes of op t
   for (uint64_t idx = lo; idx <= hi; ++idx) {
     R* row = tab.data() + (idx - lo) * len;
     // a span strictly inside (lo, hi) is only ever selected when it has positive width
@@ -294,7 +295,10 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
         const R left = kn[j + rr - 1];                 // knots[i - 1]
         const R den = kn[p + j] - left;                // knots[i + p - r] - knots[i - 1]
         if (needed) {
-          if (!(is_pow2(den) && den >= R(1e-30) && den <= R(1e30))) all_pow2 = false;
+          if (!(is_pow2(den) && den >= R(1e-30) && den <= R(1e30))) {
+            all_pow2 = false;
+            op_pow2 &= ~(1u << t);
+          }
           if (!den_in_window(den)) all_window = false;
         }
         row[t * W + l] = left;
@@ -383,6 +387,7 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
     r.rows_mode = 2;
   else
     return;
+  r.rows_pow2_ops = op_pow2;
   r.rows_n = (uint32_t)n_rows;
   r.rows_lo = (uint32_t)lo;
   r.rows_len = (uint32_t)len;

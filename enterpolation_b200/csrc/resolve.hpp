@@ -73,6 +73,7 @@ struct Resolved {
   // from tabulated reciprocals.
   int32_t rows_mode = 0;
   uint32_t rows_n = 0, rows_lo = 0, rows_len = 0;
+  uint32_t rows_pow2_ops = 0;  // exact-division rows: factor operations whose denominators are powers of two in every row
   std::vector<unsigned char> rows;
   // equidistant span division (x - offset) / step: 0 IEEE divide, 1 exact inverse multiply, 2 exact
   // division from eq_rstep = RN(1 / step)

@@ -191,6 +191,18 @@ __device__ __forceinline__ R apply_pre_outlined(const CurveDev<R>& c, R x) {
   return apply_pre_list<R>(p, x);
 }
 
+// factor operations all of whose lanes belong to de Boor levels r >= 2
+__host__ __device__ constexpr uint32_t upper_ops(int P, int W) {
+  const FactorSched sch = make_sched(P, W);
+  uint32_t m = 0;
+  for (int t = 0; t < sch.nops; ++t) {
+    bool up = true;
+    for (int l = 0; l < W; ++l) up = up && sch.r[t][l] >= 2;
+    if (up) m |= 1u << t;
+  }
+  return m;
+}
+
 constexpr int ROWS_S = 2;  // samples per thread per loop trip (block-strided, so stores stay coalesced)
 
 // CHUNK: every CTA walks ONE contiguous range of tiles instead of striding the whole grid, so a thread's
@@ -238,6 +250,7 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
   const R* __restrict__ tp = TAKE ? nullptr : s.t + i0;
   R* __restrict__ op = out + i0 * D;
 
+  const bool upper_pow2 = !POW2 && upper_ops(DEG, W) != 0u && (rw.pow2_ops & upper_ops(DEG, W)) == upper_ops(DEG, W);
   R row[ROW];
   uint32_t cached = 0xFFFFFFFFu;
   const T one2 = P::bcast(rw.one);
@@ -261,7 +274,13 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
         fac[t] = P::mul(num, y);
       } else {
         const T nd = P::make(row[2 * NOPS * W + t * W], row[2 * NOPS * W + t * W + (W - 1)]);
-        fac[t] = exact_div<R>(num, y, nd);
+        // Uniform knots with a power-of-two step: the upper de Boor levels (r >= 2) divide by powers of two in
+        // every row (C1: three of its six factors); those multiply by the exact inverse. ONE launch-uniform test
+        // per sample (upper_pow2) selects between two unrolled schedules, not one test per operation.
+        if (upper_pow2 && ((upper_ops(DEG, W) >> t) & 1u))
+          fac[t] = P::mul(num, y);
+        else
+          fac[t] = exact_div<R>(num, y, nd);
         // Range guard of the exact division with two compares per sample: the left knots of a span are
         // ascending (kl_0 <= .. <= kl_{p-1}), so x - kl_{p-1} >= 2^-40 bounds every numerator from below
         // and x - kl_0 <= 2^40 from above. Anything else (x on or left of a knot, far right, NaN, inf)
