@@ -646,3 +646,33 @@ def test_bucket_index_search(scalar, shape):
     t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
     check_curve(Linear.builder().elements(rand_elements(n, 3, dtype, 0xD4)).knots(k), t, what=f"linear {shape}")
     check_curve(BSpline.builder().elements(rand_elements(n - 2, 2, dtype, 0xD5)).knots(k).constant(4), t, what=f"bspline {shape}")
+
+
+def test_launches_are_cuda_graph_capturable():
+    """Small takes are launch-latency bound (C1 at 2^20 samples: ~16 us); after the one-time upload every eval call
+    only enqueues kernels on the caller's stream, so a sequence of them can be captured into a CUDA graph and replayed."""
+    curves = [_c5_like("f32", 7, 4),
+              Linear.builder().elements(rand_elements(12, 3, np.float32, 0x95)).knots(sorted_knots(12, np.float32, 0x96)),
+              Bezier.builder().elements(rand_elements(4, 2, np.float64, 0x97)).normalized("f64").constant(),
+              BSpline.builder().elements(rand_elements(9, 1, np.float64, 0x98)).knots(sorted_knots(11, np.float64, 0x99)).constant(4)]
+    built = [b.build() for b in curves]
+    refs = [oracle.OracleCurve(b.to_desc()) for b in curves]
+    n = 4099
+    outs = [c.take_device(n) for c in built]  # warm-up: uploads the tables, outside the capture
+    t = [torch.from_numpy(u01(n, 0x9A + i, c.dtype)).cuda() for i, c in enumerate(built)]
+    bouts = [c.sample_device(t[i]) for i, c in enumerate(built)]
+    for o in outs + bouts:
+        o.zero_()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i, c in enumerate(built):
+            c.take_device(n, out=outs[i])
+            c.sample_device(t[i], out=bouts[i])
+    for o in outs + bouts:
+        o.zero_()  # the capture itself must not have run anything we rely on
+    g.replay()
+    torch.cuda.synchronize()
+    for i, r in enumerate(refs):
+        assert_bits_equal(outs[i].cpu().numpy(), r.take(n), f"graph take {i}")
+        assert_bits_equal(bouts[i].cpu().numpy(), r.eval(t[i].cpu().numpy()), f"graph batch {i}")

@@ -41,3 +41,21 @@ timeit(lambda: cc.take_device(n, out=out4), n, "same curve .clamp() take (checke
 c = BSpline.builder().clamped().elements(bench.u01(12, 2, np.float32)).equidistant("f32").degree(5).normalized().dynamic().build()
 out1 = torch.empty(n, dtype=torch.float32, device="cuda")
 timeit(lambda: c.take_device(n, out=out1), n, "quintic equidistant f32 scalar take (rows)", 4)
+
+# launch-bound regime: 200 takes of 2^14 samples, direct calls vs one CUDA graph replay
+c = BSpline.builder().clamped().elements(el4[:9]).equidistant("f32").degree(3).normalized().dynamic().build()
+small = [torch.empty((1 << 14, 4), dtype=torch.float32, device="cuda") for _ in range(200)]
+def direct():
+    for o in small:
+        c.take_device(1 << 14, out=o)
+direct(); torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    direct()
+for name, f in (("direct calls", direct), ("CUDA graph replay", g.replay)):
+    f(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): f()
+    e1.record(); torch.cuda.synchronize()
+    print(f"200 x take(2^14) cubic [f32;4], {name:18s} {e0.elapsed_time(e1) / 10 / 200 * 1e3:7.2f} us per take")
