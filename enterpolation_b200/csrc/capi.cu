@@ -6,7 +6,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -32,6 +34,41 @@ int sm_count() {
     cache[dev] = n;
   }
   return cache[dev];
+}
+
+int cached_occupancy(const void* kernel, int block, size_t smem, size_t opt_in_smem, cudaError_t* err) {
+  struct Key {
+    const void* k;
+    int dev, block;
+    size_t smem;
+    bool operator<(const Key& o) const { return std::tie(k, dev, block, smem) < std::tie(o.k, o.dev, o.block, o.smem); }
+  };
+  static std::mutex mu;
+  static std::map<Key, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const Key key{kernel, dev, block, smem};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  if (opt_in_smem > 0) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)opt_in_smem);
+    if (e != cudaSuccess) {
+      if (err) *err = e;
+      return 1;
+    }
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;  // not cached: a transient failure must not stick
+    return per_sm;
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  cache[key] = per_sm;
+  return per_sm;
 }
 
 // Debug/ablation switch (env ENTERP_DISABLE_ROWS=1): route B-splines through the generic kernel.

@@ -24,10 +24,6 @@ cudaError_t launch_searching(K kernel, unsigned long long work_items, size_t sme
     cudaFuncAttributes fa{};
     cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
     if (e != cudaSuccess) return e;
-    if (smem > 48u * 1024u) {
-      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM_MAX);
-      if (e != cudaSuccess) return e;
-    }
     if (smem > 32u * 1024u) {  // few CTAs per SM fit: make them fat
       int cap = fa.maxThreadsPerBlock < MAX_BLOCK ? fa.maxThreadsPerBlock : MAX_BLOCK;
       const int by_regs = fa.numRegs > 0 ? (65536 / fa.numRegs) / 256 * 256 : cap;
@@ -35,8 +31,10 @@ cudaError_t launch_searching(K kernel, unsigned long long work_items, size_t sme
       block = cap >= 256 ? cap : 256;
     }
   }
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  cudaError_t eo = cudaSuccess;
+  const int per_sm =
+      cached_occupancy(reinterpret_cast<const void*>(kernel), block, smem, smem > 48u * 1024u ? SEARCH_SMEM_MAX : 0, &eo);
+  if (eo != cudaSuccess) return eo;
   unsigned long long want = (work_items + block - 1) / block;
   const unsigned long long cap_grid = (unsigned long long)per_sm * (unsigned long long)sm_count();
   const int grid = (int)(want < cap_grid ? want : cap_grid);

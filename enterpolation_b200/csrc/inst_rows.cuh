@@ -11,13 +11,9 @@ namespace enterp {
 template <class K, class R>
 cudaError_t rows_launch_kernel(K kernel, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, const RowsDev<R>& rw,
                                size_t smem, cudaStream_t st) {
-  if (smem > 0) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_MAX_BYTES);
-    if (e != cudaSuccess) return e;
-  }
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, smem) != cudaSuccess || per_sm < 1)
-    per_sm = 1;
+  cudaError_t e = cudaSuccess;
+  const int per_sm = cached_occupancy(reinterpret_cast<const void*>(kernel), BLOCK, smem, smem > 0 ? ROWS_MAX_BYTES : 0, &e);
+  if (e != cudaSuccess) return e;
   const unsigned long long want = (s.count + ROWS_S * BLOCK - 1) / (ROWS_S * BLOCK);
   const unsigned long long cap = (unsigned long long)per_sm * (unsigned long long)sm_count();
   const int grid = (int)(want < cap ? want : cap);

@@ -13,12 +13,17 @@ void count_launch();
 // SM count of the current device (cached per device).
 int sm_count();
 
+// Resident CTAs per SM of `kernel` at (block, smem) on the current device, cached: the occupancy query (and the
+// opt-in to > 48 KB of dynamic shared memory it needs first) costs microseconds, which is most of a small launch.
+// `opt_in_smem` > 0 raises cudaFuncAttributeMaxDynamicSharedMemorySize to that value once per (kernel, device).
+int cached_occupancy(const void* kernel, int block, size_t smem, size_t opt_in_smem, cudaError_t* err);
+
 // Grid for a grid-stride kernel: enough CTAs to fill every SM at the kernel's own occupancy, never
 // more than the work needs. `kernel` is the __global__ function pointer.
 template <class K>
 int grid_for(K kernel, unsigned long long work_items, int items_per_block) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  cudaError_t e = cudaSuccess;
+  const int per_sm = cached_occupancy(reinterpret_cast<const void*>(kernel), BLOCK, 0, 0, &e);
   unsigned long long want = (work_items + items_per_block - 1) / items_per_block;
   unsigned long long cap = (unsigned long long)per_sm * (unsigned long long)sm_count();
   if (want < 1) want = 1;
