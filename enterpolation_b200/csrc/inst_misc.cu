@@ -1,4 +1,6 @@
 // Linear, span, stepper and many-Bezier instantiations (both scalar types).
+#include <cstdint>
+
 #include "inst_common.cuh"
 
 namespace enterp {
@@ -45,9 +47,42 @@ static cudaError_t launch_span_impl(int kind, bool equi, const CurveDev<R>& c, c
   return launch_grid_stride(span_kernel<R, 1, true>, s.count, BLOCK, st, c, s, idx, factor);
 }
 
+// Flattened (curve, sample) mapping for few samples per curve (kernels.cuh). Returns false when it does not apply.
+template <class R, int D>
+static bool many_flat(int n, const R* ctrl, unsigned long long n_curves, uint32_t samples, R step, R* out, cudaStream_t st,
+                      cudaError_t* err) {
+  const unsigned long long total = n_curves * (unsigned long long)samples;
+  if (n < 1 || n > 16 || total >= (1ull << 32) - (1ull << 24)) return false;
+  // One warp per curve pays a dependent control-point load per curve and idles lanes when samples % 32 != 0; it wins
+  // only where that is amortised: long sample runs, or big curves whose arithmetic dwarfs the flat kernel's per-sample
+  // control loads (measured: C3 16x3x256 31.7 vs 28.9 G samples/s, 8x1x1024 348 vs 291; but 4x3x256 235 vs 342,
+  // 16x3x16 13 vs 29, 4x3x4 29 vs 234).
+  if (samples >= 128 && (n * D > 16 || samples >= 1024)) return false;
+  if ((reinterpret_cast<uintptr_t>(ctrl) % 16u) != 0) return false;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 16u) == 0;
+  // multiply-shift division by `samples` (Granlund & Montgomery, unsigned 32-bit)
+  uint32_t l = 0;
+  while ((1ull << l) < samples) ++l;
+  const uint32_t magic = (uint32_t)(((1ull << 32) * ((1ull << l) - samples)) / samples + 1);
+  const uint32_t sh1 = l < 1 ? l : 1, sh2 = l > 0 ? l - 1 : 0;
+#define ENTERP_BF(NN)                                                                                                 \
+  case NN:                                                                                                            \
+    *err = launch_grid_stride(bezier_many_flat_kernel<R, D, NN>, total, BLOCK, st, ctrl, (uint32_t)total, samples,    \
+                              magic, sh1, sh2, step, out, vec_ok);                                                    \
+    return true;
+  switch (n) {
+    ENTERP_BF(1) ENTERP_BF(2) ENTERP_BF(3) ENTERP_BF(4) ENTERP_BF(5) ENTERP_BF(6) ENTERP_BF(7) ENTERP_BF(8)
+    ENTERP_BF(9) ENTERP_BF(10) ENTERP_BF(11) ENTERP_BF(12) ENTERP_BF(13) ENTERP_BF(14) ENTERP_BF(15) ENTERP_BF(16)
+  }
+#undef ENTERP_BF
+  return false;
+}
+
 template <class R, int D>
 static cudaError_t many_pick_n(int n, const R* ctrl, unsigned long long n_curves, uint32_t n_ctrl, uint32_t samples,
                                R step, R* out, cudaStream_t st) {
+  cudaError_t fe = cudaSuccess;
+  if (many_flat<R, D>(n, ctrl, n_curves, samples, step, out, st, &fe)) return fe;
   // one warp per curve -> BLOCK/32 curves per block
 #define ENTERP_BM(NN) \
   case NN: return launch_grid_stride(bezier_many_kernel<R, D, NN>, n_curves, BLOCK / 32, st, ctrl, n_curves, n_ctrl, samples, step, out);

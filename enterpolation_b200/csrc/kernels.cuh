@@ -700,13 +700,21 @@ __global__ void __launch_bounds__(BLOCK) bezier_many_kernel(const R* __restrict_
   for (unsigned long long curve = (((unsigned long long)blockIdx.x * BLOCK + threadIdx.x) >> 5); curve < n_curves;
        curve += warps) {
     const R* __restrict__ cp = ctrl + curve * (unsigned long long)n * D;
+    // small curves: the control values are read once per curve, not once per sample (a cubic has 54 flops per
+    // sample; twelve loads beside them made the kernel LSU-bound)
+    constexpr bool HOIST = N > 0 && N * D <= 16;
+    R held[HOIST ? N_CAP * D : 1];
+    if constexpr (HOIST) {
+#pragma unroll
+      for (int m = 0; m < N_CAP * D; ++m) held[m] = __ldg(cp + m);
+    }
     for (uint32_t sidx = lane; sidx < samples; sidx += 32u) {
       const R x = xadd(xmul(step, from_index(sidx, R(0))), R(0));  // Stepper over [0,1]
       const R omx = xsub(R(1), x);
       R ws[N_CAP * D];
       if (N > 0) {
 #pragma unroll
-        for (int m = 0; m < N_CAP * D; ++m) ws[m] = __ldg(cp + m);
+        for (int m = 0; m < N_CAP * D; ++m) ws[m] = HOIST ? held[HOIST ? m : 0] : __ldg(cp + m);
 #pragma unroll
         for (int k = 1; k <= N_CAP - 1; ++k)
 #pragma unroll
@@ -724,6 +732,43 @@ __global__ void __launch_bounds__(BLOCK) bezier_many_kernel(const R* __restrict_
 #pragma unroll
       for (int q = 0; q < D; ++q) __stcs(p + q, ws[q]);
     }
+  }
+}
+
+// Few samples per curve: one warp per curve would idle most lanes (4 samples: 28 of 32), so the (curve, sample)
+// pairs are flattened and every thread takes one pair; neighbouring threads share a curve's control values through
+// L1. `total` = n_curves * samples < 2^32 - 2^24; the division by `samples` is the multiply-shift form
+// (Granlund & Montgomery): q = (t + ((i - t) >> sh1)) >> sh2 with t = umulhi(magic, i).
+template <class R, int D, int N>
+__global__ void __launch_bounds__(BLOCK) bezier_many_flat_kernel(const R* __restrict__ ctrl, uint32_t total,
+                                                                 uint32_t samples, uint32_t magic, uint32_t sh1,
+                                                                 uint32_t sh2, R step, R* __restrict__ out, bool vec_ok) {
+  static_assert(N > 0, "compile-time control point count");
+  const uint32_t stride = gridDim.x * BLOCK;
+  for (uint32_t i = blockIdx.x * BLOCK + threadIdx.x; i < total; i += stride) {
+    const uint32_t t = __umulhi(magic, i);
+    const uint32_t curve = (t + ((i - t) >> sh1)) >> sh2;
+    const uint32_t sidx = i - curve * samples;
+    const R x = xadd(xmul(step, from_index(sidx, R(0))), R(0));  // Stepper over [0,1]
+    const R omx = xsub(R(1), x);
+    const R* __restrict__ cp = ctrl + (size_t)curve * (N * D);
+    R ws[N * D];
+    if constexpr ((N * D * (int)sizeof(R)) % 16 == 0) {
+      load_vec<N * D, false>(cp, ws);  // curves are N*D*sizeof(R) apart: 16-byte aligned when the base is
+    } else {
+#pragma unroll
+      for (int m = 0; m < N * D; ++m) ws[m] = __ldg(cp + m);
+    }
+#pragma unroll
+    for (int k = 1; k <= N - 1; ++k)
+#pragma unroll
+      for (int j = 0; j < N - k; ++j)
+#pragma unroll
+        for (int q = 0; q < D; ++q) ws[j * D + q] = merge1(ws[j * D + q], ws[(j + 1) * D + q], x, omx);
+    R v[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) v[q] = ws[q];
+    store_elem<R, D>(out, i, v, vec_ok);
   }
 }
 

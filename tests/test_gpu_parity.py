@@ -211,6 +211,24 @@ def test_bezier_many(scalar, n_ctrl, dim):
     assert_bits_equal(np.asarray(c0.take(samples).collect()).reshape(samples, dim), got[5], "many == single")
 
 
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("n_ctrl,dim", [(1, 3), (2, 2), (3, 4), (4, 3), (4, 1), (8, 2), (9, 3), (16, 3)])
+@pytest.mark.parametrize("samples", [2, 3, 4, 7, 31, 32, 33, 64, 127, 128, 300])
+def test_bezier_many_small_sample_counts(scalar, n_ctrl, dim, samples):
+    """Few samples per curve take the flattened (curve, sample) kernel with its multiply-shift division; larger counts
+    the warp-per-curve kernel (control values hoisted for small curves). Odd curve counts leave ragged tails."""
+    dtype = DT[scalar]
+    n_curves = 1031
+    ctrl = rand_elements(n_curves * n_ctrl, dim, dtype, 0xF7 + samples).reshape(n_curves, n_ctrl, dim)
+    got = bezier_many_take(torch.from_numpy(ctrl).cuda(), samples).cpu().numpy()
+    assert_bits_equal(got, oracle.bezier_many_take(ctrl, samples), f"bezier_many {scalar} n{n_ctrl} d{dim} s{samples}")
+    # a misaligned control array keeps the scalar-load kernel
+    buf = torch.empty(ctrl.size + 1, dtype=torch.from_numpy(ctrl).dtype, device="cuda")
+    view = buf[1:].view(n_curves, n_ctrl, dim)
+    view.copy_(torch.from_numpy(ctrl))
+    assert_bits_equal(bezier_many_take(view, samples).cpu().numpy(), got, "misaligned ctrl")
+
+
 def test_large_sorted_search_levels():
     """4-level pivot pyramid (70 000 knots): exact knots + neighbours + random, f32 Linear [f32;3]."""
     dtype = np.float32
