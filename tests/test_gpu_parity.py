@@ -400,6 +400,28 @@ def test_misaligned_output_pointer_uses_scalar_stores():
     assert_bits_equal(out.cpu().numpy(), r.eval(t), "misaligned batch")
 
 
+def test_f64x4_output_alignment_classes():
+    """[f64;4] samples are written with one 256-bit store when the output is 32-byte aligned, two 128-bit stores at
+    16-byte alignment, scalar stores below that (kernels.cuh store_elem)."""
+    el = rand_elements(12, 4, np.float64, 0x84)
+    for b in (Linear.builder().elements(el).equidistant("f64").normalized(),
+              Bezier.builder().elements(el[:5]).normalized("f64").constant(),
+              BSpline.builder().clamped().elements(el).equidistant("f64").degree(2).normalized().dynamic()):
+        c, r = b.build(), oracle.OracleCurve(b.to_desc())
+        n = 1000
+        want = r.take(n)
+        t = u01(n, 0x85, np.float64)
+        for offset in (0, 2, 1):  # doubles: 32-, 16-, 8-byte aligned
+            buf = torch.zeros(n * 4 + 4, dtype=torch.float64, device="cuda")
+            out = buf[offset:offset + n * 4].view(n, 4)
+            assert out.data_ptr() % 32 == (offset * 8) % 32
+            c.take_device(n, out=out)
+            assert_bits_equal(out.cpu().numpy(), want, f"take, offset {offset}")
+            c.sample_device(torch.from_numpy(t).cuda(), out=out)
+            assert_bits_equal(out.cpu().numpy(), r.eval(t), f"batch, offset {offset}")
+            assert float(buf[offset + n * 4:].abs().sum()) == 0.0 and float(buf[:offset].abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize("scalar", ["f32", "f64"])
 def test_huge_global_index_range(scalar):
     """take(2^40): 64-bit global indices and fl(i) beyond 2^32 (shards of a very long stepper)."""
