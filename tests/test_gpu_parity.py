@@ -716,3 +716,45 @@ def test_launches_are_cuda_graph_capturable():
     for i, r in enumerate(refs):
         assert_bits_equal(outs[i].cpu().numpy(), r.take(n), f"graph take {i}")
         assert_bits_equal(bouts[i].cpu().numpy(), r.eval(t[i].cpu().numpy()), f"graph batch {i}")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("knots_kind", ["equidistant", "equidistant_pow2", "sorted"])
+def test_hold_intervals_at_every_float_around_the_knots(scalar, knots_kind):
+    """The chunked take variants skip the span computation while hold_lo <= x < hold_hi. Zooming a slice onto each knot
+    (parameter spacing far below one ulp) walks through every representable parameter on both sides of every span
+    boundary, where a hold interval that is off by a single float would pick the wrong row."""
+    dtype = DT[scalar]
+    stops, degree = 11, 3
+    el = rand_elements(stops, 2, dtype, 0xC7)
+    b = BSpline.builder().clamped().elements(el)
+    if knots_kind == "sorted":
+        b = b.knots(sorted_knots(stops - degree + 1, dtype, 0xC8))
+    elif knots_kind == "equidistant":
+        b = b.equidistant(scalar).degree(degree).domain(-1.0, 2.0)   # step 3/8... not a power of two after rounding
+    else:
+        b = b.equidistant(scalar).degree(degree).normalized()        # 8 intervals: step 2^-3
+    b = b.dynamic()
+    c, r = b.build(), oracle.OracleCurve(b.to_desc())
+    d = r.domain()
+    n_inner = stops - degree + 1
+    if knots_kind == "sorted":
+        knots = sorted_knots(n_inner, dtype, 0xC8)
+    else:
+        knots = np.linspace(float(d[0]), float(d[1]), n_inner).astype(dtype)
+    eps = 64 * float(np.finfo(dtype).eps)
+    for k in knots:
+        lo, hi = float(k) - eps * max(1.0, abs(float(k))), float(k) + eps * max(1.0, abs(float(k)))
+        cs, rs = c.slice(lo, hi), r.slice(lo, hi)
+        assert_bits_equal(cs.take_device(8192).cpu().numpy(), rs.take(8192), f"zoom on knot {k}")
+    if scalar == "f32":  # plain take(): a stepper finer than one ulp, windows centred on every knot
+        n_total = 1 << 31
+        step = (float(d[1]) - float(d[0])) / (n_total - 1)
+        for k in knots[1:-1]:
+            first = int(round((float(k) - float(d[0])) / step)) - 2048
+            assert_bits_equal(c.take_device(n_total, first, 4096).cpu().numpy(), r.take(n_total, first, 4096), f"window on {k}")
+        lin = Linear.builder().elements(rand_elements(n_inner, 3, dtype, 0xC9)).knots(np.asarray(knots, dtype=dtype))
+        lc, lr = lin.build(), oracle.OracleCurve(lin.to_desc())
+        for k in knots[1:-1]:
+            first = int(round((float(k) - float(d[0])) / step)) - 2048
+            assert_bits_equal(lc.take_device(n_total, first, 4096).cpu().numpy(), lr.take(n_total, first, 4096), f"linear window on {k}")
