@@ -56,14 +56,18 @@ cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
   // knots (a pivot search), exact-division rows (C1: 205 vs 182 G samples/s) — and is the only one for tables
   // beyond the shared-memory budget. Power-of-two equidistant rows that fit (C5) measure the same either way
   // (309 vs 307 G samples/s at 2^32, 261 vs 268 at 2^24) and keep the shared-memory variant.
-  if (s.t == nullptr && !need_check && (!EQUI || !POW2 || !fits || rows_force_chunk()))
+  constexpr bool HAS_V2 = EQUI && POW2;  // the only rows for which variant 2 is ever chosen: not instantiated elsewhere
+  if (s.t == nullptr && !need_check && (!HAS_V2 || !fits || rows_force_chunk()))
     return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 3>, c, s, out, rw, 0, st);
   if (s.t == nullptr && need_check)  // adaptors / possible panics: same chunked walk with the per-sample checks
     return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 1>, c, s, out, rw, 0, st);
   if (!fits) return cudaErrorNotSupported;  // big table and a batch: the caller falls back to the generic kernel
   if (s.t != nullptr)
     return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 0>, c, s, out, rw, rw.bytes, st);
-  return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 2>, c, s, out, rw, rw.bytes, st);
+  if constexpr (HAS_V2)
+    return rows_launch_kernel(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 2>, c, s, out, rw, rw.bytes, st);
+  else
+    return cudaErrorNotSupported;  // unreachable: handled by variant 3 above
 }
 
 template <class R, int DH, bool PROJ, bool EQUI, bool POW2>
