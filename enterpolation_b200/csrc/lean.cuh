@@ -26,6 +26,48 @@ __device__ __forceinline__ double from_u32(uint32_t i, double) { return __uint2d
 __device__ __forceinline__ uint32_t to_u32(float v) { return __float2uint_rz(v); }
 __device__ __forceinline__ uint32_t to_u32(double v) { return __double2uint_rz(v); }
 
+// Three-component elements (12 / 24 bytes) cannot be stored with one vector instruction per thread: three narrow
+// stores per warp write every 32-byte sector of the warp's 384 / 768 contiguous bytes in two or three partial pieces.
+// When the whole warp is converged on 32 consecutive samples, the 96 values are transposed through shared memory
+// and leave as full 128-bit stores. `stage`: this warp's 96 values; `i0`: sample index of lane 0.
+template <class R>
+__device__ __forceinline__ void store_warp3(R* __restrict__ out, uint32_t i0, const R (&v)[3], R* stage) {
+  const unsigned lane = threadIdx.x & 31u;
+  stage[3 * lane] = v[0];
+  stage[3 * lane + 1] = v[1];
+  stage[3 * lane + 2] = v[2];
+  __syncwarp();
+  constexpr unsigned N16 = 96u * (unsigned)sizeof(R) / 16u;  // 24 (f32) / 48 (f64) 128-bit pieces
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)i0 * 3);
+  const float4* src = reinterpret_cast<const float4*>(stage);
+#pragma unroll
+  for (unsigned k = 0; k < (N16 + 31u) / 32u; ++k) {
+    const unsigned q = lane + 32u * k;
+    if (q < N16) __stcs(dst + q, src[q]);
+  }
+  __syncwarp();
+}
+// Measured (take(2^26..28), tools/sweep_perf.py): plain [f64;3] gains 20-55 % (Linear 210 -> 251, sorted-knot Linear
+// 157 -> 243, cubic Bezier 196 -> 236 G samples/s); [f32;3] loses 8-16 % (its three 32-bit stores already reach 86-90 % of
+// the HBM roof) and weighted curves lose 5-10 % (bound by the projection divisions) — so only plain [f64;3] uses it.
+template <class R, int D, bool PROJ>
+__host__ __device__ constexpr bool lean_transposed_store() { return D == 3 && sizeof(R) == 8 && !PROJ; }
+// store of one sample in the lean kernels (output 16-byte aligned, host-checked); `stage3`: BLOCK/32 * 96 values
+template <class R, int D, bool PROJ>
+__device__ __forceinline__ void lean_store(R* __restrict__ out, uint32_t i, const R (&v)[D], R* stage3) {
+  if constexpr (lean_transposed_store<R, D, PROJ>()) {
+    if (__activemask() == 0xffffffffu) {
+      store_warp3<R>(out, i - (threadIdx.x & 31u), v, stage3 + (threadIdx.x >> 5) * 96);
+      return;
+    }
+  }
+  store_elem<R, D>(out, i, v, true);
+}
+template <class R, int D, bool PROJ>
+struct LeanStage {
+  static constexpr int N = lean_transposed_store<R, D, PROJ>() ? (BLOCK / 32) * 96 : 4;
+};
+
 template <class R>
 struct LeanTake {
   R step, start;    // t_i = step * fl(first + i) + start (list.rs:416-418)
@@ -87,6 +129,7 @@ __device__ __forceinline__ R lean_easing(const LeanLinear<R>& c, R f) {
 template <class R, int DH, bool PROJ, int MODE, bool EASE, bool BATCH>
 __global__ void __launch_bounds__(BLOCK) linear_equi_lean_kernel(const LeanLinear<R> c, const LeanTake<R> s,
                                                                  const R* __restrict__ t, R* __restrict__ out) {
+  __shared__ __align__(16) R stage3[LeanStage<R, PROJ ? DH - 1 : DH, PROJ>::N];
   const uint32_t stride = gridDim.x * BLOCK;
   for (uint32_t i = blockIdx.x * BLOCK + threadIdx.x; i < s.count; i += stride) {
     const R x = BATCH ? __ldcs(t + i) : xadd(xmul(s.step, from_u32(s.first + i, R(0))), s.start);
@@ -136,7 +179,7 @@ __global__ void __launch_bounds__(BLOCK) linear_equi_lean_kernel(const LeanLinea
         atomicAdd(c.invalid, 1ull);
       }
     }
-    store_elem<R, D>(out, i, v, true);
+    lean_store<R, D, PROJ>(out, i, v, stage3);
   }
 }
 
@@ -152,6 +195,7 @@ template <class R, int DH, bool PROJ, bool EASE>
 __global__ void __launch_bounds__(BLOCK, 4) linear_sorted_take_kernel(const CurveDev<R> c, const LeanLinear<R> l,
                                                                    const LeanTake<R> s, R* __restrict__ out) {
   constexpr int STRIDE = linear_rec_stride<R>(DH);
+  __shared__ __align__(16) R stage3[LeanStage<R, PROJ ? DH - 1 : DH, PROJ>::N];
   const uint32_t tiles = (s.count + BLOCK - 1) / BLOCK;
   const uint32_t per = (tiles + gridDim.x - 1) / gridDim.x;
   const uint32_t t0 = blockIdx.x * per;
@@ -184,7 +228,7 @@ __global__ void __launch_bounds__(BLOCK, 4) linear_sorted_take_kernel(const Curv
     R v[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) v[k] = PROJ ? xdiv(w[k], w[DH - 1]) : w[k];
-    store_elem<R, D>(out, i, v, true);
+    lean_store<R, D, PROJ>(out, i, v, stage3);
   }
 }
 
@@ -202,6 +246,7 @@ struct LeanBezier {
 template <class R, int DH, bool PROJ, int N, bool BATCH>
 __global__ void __launch_bounds__(BLOCK) bezier_lean_kernel(const LeanBezier<R, N * DH> c, const LeanTake<R> s,
                                                             const R* __restrict__ t, R* __restrict__ out) {
+  __shared__ __align__(16) R stage3[LeanStage<R, PROJ ? DH - 1 : DH, PROJ>::N];
   const uint32_t stride = gridDim.x * BLOCK;
   for (uint32_t i = blockIdx.x * BLOCK + threadIdx.x; i < s.count; i += stride) {
     R x = BATCH ? __ldcs(t + i) : xadd(xmul(s.step, from_u32(s.first + i, R(0))), s.start);
@@ -220,7 +265,7 @@ __global__ void __launch_bounds__(BLOCK) bezier_lean_kernel(const LeanBezier<R, 
     R v[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) v[k] = PROJ ? xdiv(ws[k], ws[DH - 1]) : ws[k];
-    store_elem<R, D>(out, i, v, true);
+    lean_store<R, D, PROJ>(out, i, v, stage3);
   }
 }
 
