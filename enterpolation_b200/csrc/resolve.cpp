@@ -395,8 +395,9 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
   std::memcpy(r.rows.data(), tab.data(), r.rows.size());
 }
 
-// Bucket index of the sorted search (resolve.hpp). Worth it for big knot vectors only (small ones live in L1 /
-// shared memory anyway) and only when the knots spread over the buckets: the kernel compares at most
+// Bucket index of the sorted search (resolve.hpp), for 32 knots and up — small tables gain too (256 knots, random batch:
+// Linear 114 -> 160, cubic B-spline 67 -> 84 G samples/s: one L1-resident lookup instead of a three-level descent) — and only
+// when the knots spread over the buckets: the kernel compares at most
 // BUCKET_SCAN knots of a bucket and falls back to the pivot tree beyond that.
 constexpr uint32_t BUCKET_SCAN = 4;
 template <class R>
@@ -408,7 +409,7 @@ uint32_t bucket_of(R x, R first, R inv, uint32_t n_buckets) {
 template <class R>
 void build_buckets(Resolved& r, const R* knots, uint64_t n) {
   r.buckets.clear();
-  if (n < 4096 || n > (1ull << 30)) return;
+  if (n < 32 || n > (1ull << 30)) return;
   const R first = knots[0], last = knots[n - 1];
   if (!(last > first) || !std::isfinite(first) || !std::isfinite(last)) return;
   uint64_t nb = 1;
