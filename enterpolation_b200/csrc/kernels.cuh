@@ -34,7 +34,7 @@ struct CurveDev {
   int n_lvl;
   int n_top;           // levels [0, n_top) are staged into shared memory by the kernel (0: none)
   uint32_t top_bytes;  // their total size (multiple of 32)
-  // Bucket index of the searched knot range (resolve.hpp), or nullptr: n_bkt pairs {prefix count, knots in bucket}
+  // Bucket index of the searched knot range (resolve.hpp), or nullptr: n_bkt words, prefix count | count << 29
   const uint32_t* bkt;
   uint32_t n_bkt;
   R bkt_first, bkt_inv;
@@ -312,9 +312,9 @@ __device__ __forceinline__ uint32_t count_le(const CurveDev<R>& c, R x, const R*
     const R tq = xmul(xsub(x, c.bkt_first), c.bkt_inv);
     // NaN must land in bucket 0 explicitly: the f64 -> u32 conversion does not map NaN to 0 (measured on sm_100a)
     const uint32_t b = min(tq >= R(0) ? bucket_sat_u32(tq) : 0u, c.n_bkt - 1u);
-    const uint2 e = __ldg(reinterpret_cast<const uint2*>(c.bkt) + b);  // {prefix count, knots in the bucket}: one sector request
-    lo = e.x;
-    hi = e.x + e.y;
+    const uint32_t e = __ldg(c.bkt + b);  // prefix count (29 bits) | knots in the bucket, saturated at 7 (3 bits)
+    lo = e & 0x1FFFFFFFu;
+    hi = lo + (e >> 29);
     tree = hi - lo > BUCKET_SCAN;
   }
   if (tree) return count_le_tree(c, x, top);  // one call site: the unrolled descent is big

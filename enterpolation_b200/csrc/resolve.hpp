@@ -48,7 +48,7 @@ struct Resolved {
   std::vector<unsigned char> elems;
   SearchLevels levels;
   // Bucket index over the searched knot range (sorted knots): B equal-width buckets of [first, last];
-  // buckets[2b] = number of searched knots whose bucket is < b, buckets[2b+1] = knots in bucket b. bucket(x) is the monotone
+  // buckets[b] = (number of searched knots whose bucket is < b) | min(knots in bucket b, 7) << 29. bucket(x) is the monotone
   // function clamp(trunc((x - first) * inv), 0, B - 1) evaluated in R, so the knots <= x are those of the lower
   // buckets plus a compare over the few knots sharing x's bucket. Empty when the knots are too clustered for it.
   std::vector<uint32_t> buckets;
