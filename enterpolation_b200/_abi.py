@@ -25,6 +25,7 @@ INVALID_ARGUMENT = 10
 UNSUPPORTED = 11
 NO_DEVICE = 12
 CUDA_ERROR = 13
+NOT_UPLOADED = 14
 
 LINEAR, BEZIER, BSPLINE = 0, 1, 2
 F32, F64 = 0, 1
@@ -83,7 +84,8 @@ EXPORTS = [
     "enterp_curve_validate", "enterp_curve_create", "enterp_curve_destroy", "enterp_curve_get_info", "enterp_curve_get_resolved", "enterp_curve_domain",
     "enterp_curve_clamp", "enterp_curve_slice", "enterp_curve_upload", "enterp_eval_batch", "enterp_eval_take", "enterp_span_batch",
     "enterp_span_take", "enterp_stepper", "enterp_bezier_many_take", "enterp_bezier_tangent_batch", "enterp_bezier_derivatives_batch", "enterp_sample_host",
-    "enterp_take_host", "enterp_host_alloc", "enterp_host_free", "enterp_invalid_count",
+    "enterp_take_host", "enterp_sample_host_multi", "enterp_take_host_multi", "enterp_host_scratch_release",
+    "enterp_host_alloc", "enterp_host_free", "enterp_invalid_count", "enterp_invalid_count_stream", "enterp_invalid_reset",
     "enterp_status_str", "enterp_last_cuda_error", "enterp_device_count", "enterp_launch_count",
     "enterp_version",
 ]
@@ -146,6 +148,16 @@ def load_library() -> C.CDLL:
     lib.enterp_sample_host.restype = i32
     lib.enterp_take_host.argtypes = [vp, i32, u64, u64, u64, vp]
     lib.enterp_take_host.restype = i32
+    lib.enterp_sample_host_multi.argtypes = [vp, C.POINTER(C.c_int), i32, vp, u64, vp]
+    lib.enterp_sample_host_multi.restype = i32
+    lib.enterp_take_host_multi.argtypes = [vp, C.POINTER(C.c_int), i32, u64, u64, u64, vp]
+    lib.enterp_take_host_multi.restype = i32
+    lib.enterp_host_scratch_release.argtypes = [i32]
+    lib.enterp_host_scratch_release.restype = i32
+    lib.enterp_invalid_count_stream.argtypes = [vp, i32, vp, C.POINTER(C.c_ulonglong)]
+    lib.enterp_invalid_count_stream.restype = i32
+    lib.enterp_invalid_reset.argtypes = [vp, i32, vp]
+    lib.enterp_invalid_reset.restype = i32
     lib.enterp_host_alloc.argtypes = [C.POINTER(vp), u64]
     lib.enterp_host_alloc.restype = i32
     lib.enterp_host_free.argtypes = [vp]

@@ -127,18 +127,21 @@ struct DeviceGuard {
   }
 };
 
-// Scratch of the host-buffer pipelines (double buffered): one per DEVICE, shared by every curve, so
-// that a freshly built curve does not pay for device/pinned allocations (a build() + collect() step
-// is then bound by PCIe alone). Calls on one device serialise on the pipe's mutex.
+// Scratch of the host-buffer pipelines (double buffered). Pipes are pooled per DEVICE and shared by every curve,
+// so that a freshly built curve does not pay for device/pinned allocations (a build() + collect() step is then
+// bound by PCIe alone). A call borrows an idle pipe (or creates one): concurrent host-buffer callers on one
+// device no longer serialise on a single mutex; idle pipes are freed by enterp_host_scratch_release().
+// Every buffer carries its OWN size, reset to 0 whenever the buffer is freed, so a failed (re)allocation can
+// never leave a null pointer behind a non-zero recorded size.
+struct HostBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
 struct HostPipe {
-  void* dev_in[2] = {nullptr, nullptr};
-  void* dev_out[2] = {nullptr, nullptr};
-  void* stage_in[2] = {nullptr, nullptr};
-  void* stage_out[2] = {nullptr, nullptr};
-  size_t dev_in_bytes = 0, dev_out_bytes = 0, stage_in_bytes = 0, stage_out_bytes = 0;
+  HostBuf dev_in[2], dev_out[2], stage_in[2], stage_out[2];
   cudaStream_t stream[2] = {nullptr, nullptr};
   cudaEvent_t done[2] = {nullptr, nullptr};
-  std::mutex mu;
+  bool busy = false;
 };
 
 struct Replica {
@@ -158,13 +161,68 @@ struct Replica {
   unsigned long long* invalid = nullptr;
 };
 
-static HostPipe* device_pipe(int device) {
-  static std::mutex mu;
-  static std::vector<HostPipe*> pipes;
-  std::lock_guard<std::mutex> lk(mu);
-  if ((int)pipes.size() <= device) pipes.resize(device + 1, nullptr);
-  if (!pipes[device]) pipes[device] = new HostPipe();  // lives until process exit
-  return pipes[device];
+struct PipePool {
+  std::mutex mu;
+  std::vector<std::vector<HostPipe*>> by_device;
+};
+static PipePool& pipe_pool() {
+  static PipePool* pool = new PipePool();  // lives until process exit (no static-destruction order games with CUDA)
+  return *pool;
+}
+static HostPipe* acquire_pipe(int device) {
+  PipePool& pool = pipe_pool();
+  std::lock_guard<std::mutex> lk(pool.mu);
+  if ((int)pool.by_device.size() <= device) pool.by_device.resize(device + 1);
+  for (HostPipe* hp : pool.by_device[device])
+    if (!hp->busy) {
+      hp->busy = true;
+      return hp;
+    }
+  HostPipe* hp = new HostPipe();
+  hp->busy = true;
+  pool.by_device[device].push_back(hp);
+  return hp;
+}
+static void release_pipe(HostPipe* hp) {
+  std::lock_guard<std::mutex> lk(pipe_pool().mu);
+  hp->busy = false;
+}
+static void free_buf(HostBuf& b, bool host) {
+  if (b.p) {
+    if (host) cudaFreeHost(b.p); else cudaFree(b.p);
+  }
+  b.p = nullptr;
+  b.bytes = 0;
+}
+// Frees the idle pipes of `device` (all devices when device < 0); returns how many were freed.
+static int release_idle_pipes(int device) {
+  PipePool& pool = pipe_pool();
+  std::lock_guard<std::mutex> lk(pool.mu);
+  int freed = 0;
+  for (int d = 0; d < (int)pool.by_device.size(); ++d) {
+    if (device >= 0 && d != device) continue;
+    std::vector<HostPipe*>& v = pool.by_device[d];
+    DeviceGuard g(d);
+    for (size_t i = 0; i < v.size();) {
+      HostPipe* hp = v[i];
+      if (hp->busy) {
+        ++i;
+        continue;
+      }
+      for (int b = 0; b < 2; ++b) {
+        free_buf(hp->dev_in[b], false);
+        free_buf(hp->dev_out[b], false);
+        free_buf(hp->stage_in[b], true);
+        free_buf(hp->stage_out[b], true);
+        if (hp->stream[b]) cudaStreamDestroy(hp->stream[b]);
+        if (hp->done[b]) cudaEventDestroy(hp->done[b]);
+      }
+      delete hp;
+      v.erase(v.begin() + i);
+      ++freed;
+    }
+  }
+  return freed;
 }
 
 }  // namespace enterp
@@ -282,8 +340,17 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   return ENTERP_OK;
 }
 
-enterp_status get_replica(enterp_curve* c, int device, Replica** out) {
+// `stream`: the stream the caller is about to enqueue on. The first use of a curve on a device uploads its tables
+// with blocking cudaMalloc/cudaMemcpy calls, which are illegal while that stream is being captured into a CUDA
+// graph (they would invalidate the capture): report it instead — enterp_curve_upload() belongs before the capture.
+enterp_status get_replica(enterp_curve* c, int device, Replica** out, cudaStream_t stream = nullptr) {
   std::lock_guard<std::mutex> lk(c->core->mu);
+  const bool have = device >= 0 && device < (int)c->core->replicas.size() && c->core->replicas[device] != nullptr;
+  if (!have && stream != nullptr) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return ENTERP_NOT_UPLOADED;
+    cudaGetLastError();
+  }
   return upload_locked(c, device, out);
 }
 
@@ -424,13 +491,13 @@ enterp_status eval_common(enterp_curve* c, int device, bool take, const void* t,
   if (!c) return ENTERP_INVALID_ARGUMENT;
   if (count == 0) return ENTERP_OK;
   if (!out || (!take && !t)) return ENTERP_INVALID_ARGUMENT;
-  if (take && (n_total == 0 || first + count > n_total)) return ENTERP_INVALID_ARGUMENT;
+  if (take && (n_total == 0 || first > n_total || count > n_total - first)) return ENTERP_INVALID_ARGUMENT;
   Replica* rp = nullptr;
-  enterp_status st = get_replica(c, device, &rp);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  enterp_status st = get_replica(c, device, &rp, cs);
   if (st) return st;
   DeviceGuard g(device);
   if (!g.ok) return ENTERP_NO_DEVICE;
-  cudaStream_t cs = static_cast<cudaStream_t>(stream);
   if (c->core->r.scalar == ENTERP_F32) {
     auto s = take ? take_src<float>(c->core->r, n_total, first, count) : batch_src<float>(t, count);
     return dispatch_eval<float>(*c, *rp, s, out, cs);
@@ -444,13 +511,13 @@ enterp_status span_common(enterp_curve* c, int device, bool take, const void* t,
   if (!c) return ENTERP_INVALID_ARGUMENT;
   if (count == 0) return ENTERP_OK;
   if (!idx || (!take && !t)) return ENTERP_INVALID_ARGUMENT;
-  if (take && (n_total == 0 || first + count > n_total)) return ENTERP_INVALID_ARGUMENT;
+  if (take && (n_total == 0 || first > n_total || count > n_total - first)) return ENTERP_INVALID_ARGUMENT;
   Replica* rp = nullptr;
-  enterp_status st = get_replica(c, device, &rp);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  enterp_status st = get_replica(c, device, &rp, cs);
   if (st) return st;
   DeviceGuard g(device);
   if (!g.ok) return ENTERP_NO_DEVICE;
-  cudaStream_t cs = static_cast<cudaStream_t>(stream);
   const bool equi = c->core->r.knot_base != ENTERP_KNOTS_SORTED;
   cudaError_t e;
   if (c->core->r.scalar == ENTERP_F32) {
@@ -476,111 +543,182 @@ bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-cudaError_t ensure(void** p, size_t* have, size_t need, bool host) {
-  if (*have >= need) return cudaSuccess;
-  if (*p) {
-    if (host) cudaFreeHost(*p); else cudaFree(*p);
-    *p = nullptr;
-    *have = 0;
+cudaError_t ensure(HostBuf& b, size_t need, bool host) {
+  if (b.bytes >= need && b.p) return cudaSuccess;
+  free_buf(b, host);  // resets the recorded size together with the pointer
+  const cudaError_t e = host ? cudaMallocHost(&b.p, need) : cudaMalloc(&b.p, need);
+  if (e == cudaSuccess) {
+    b.bytes = need;
+  } else {
+    b.p = nullptr;
+    b.bytes = 0;
   }
-  cudaError_t e = host ? cudaMallocHost(p, need) : cudaMalloc(p, need);
-  if (e == cudaSuccess) *have = need;
   return e;
 }
 
-enterp_status host_common(enterp_curve* c, int device, bool take, const void* t_host, uint64_t n_total, uint64_t first,
-                          uint64_t count, void* out_host) {
-  if (!c) return ENTERP_INVALID_ARGUMENT;
-  if (count == 0) return ENTERP_OK;
-  if (!out_host || (!take && !t_host)) return ENTERP_INVALID_ARGUMENT;
-  if (take && (n_total == 0 || first + count > n_total)) return ENTERP_INVALID_ARGUMENT;
+// One device's share of a host-buffer call: samples [off0, off0 + count) of the caller's arrays (take mode: global
+// stepper indices first + off0 ...), pushed through a borrowed pipe chunk by chunk.
+struct HostLane {
+  int device = 0;
   Replica* rp = nullptr;
-  enterp_status st = get_replica(c, device, &rp);
-  if (st) return st;
-  DeviceGuard g(device);
-  if (!g.ok) return ENTERP_NO_DEVICE;
-  HostPipe& hp = *device_pipe(device);
-  std::lock_guard<std::mutex> lk(hp.mu);
-  const size_t rs = rsize(c->core->r);
-  const size_t out_stride = rs * c->core->r.dim;
-  const uint64_t chunk = count < HOST_CHUNK ? count : HOST_CHUNK;
-  const bool pin_in = take || is_pinned(t_host);
-  const bool pin_out = is_pinned(out_host);
-  for (int b = 0; b < 2; ++b) {
-    if (!hp.stream[b]) CK(cudaStreamCreateWithFlags(&hp.stream[b], cudaStreamNonBlocking), "cudaStreamCreate");
-    if (!hp.done[b]) CK(cudaEventCreateWithFlags(&hp.done[b], cudaEventDisableTiming), "cudaEventCreate");
-  }
-  {
-    size_t a = hp.dev_in_bytes, b = hp.dev_in_bytes;
-    if (!take) {
-      CK(ensure(&hp.dev_in[0], &a, chunk * rs, false), "cudaMalloc");
-      CK(ensure(&hp.dev_in[1], &b, chunk * rs, false), "cudaMalloc");
-      hp.dev_in_bytes = a < b ? a : b;
-    }
-    a = b = hp.dev_out_bytes;
-    CK(ensure(&hp.dev_out[0], &a, chunk * out_stride, false), "cudaMalloc");
-    CK(ensure(&hp.dev_out[1], &b, chunk * out_stride, false), "cudaMalloc");
-    hp.dev_out_bytes = a < b ? a : b;
-    if (!pin_in) {
-      a = b = hp.stage_in_bytes;
-      CK(ensure(&hp.stage_in[0], &a, chunk * rs, true), "cudaMallocHost");
-      CK(ensure(&hp.stage_in[1], &b, chunk * rs, true), "cudaMallocHost");
-      hp.stage_in_bytes = a < b ? a : b;
-    }
-    if (!pin_out) {
-      a = b = hp.stage_out_bytes;
-      CK(ensure(&hp.stage_out[0], &a, chunk * out_stride, true), "cudaMallocHost");
-      CK(ensure(&hp.stage_out[1], &b, chunk * out_stride, true), "cudaMallocHost");
-      hp.stage_out_bytes = a < b ? a : b;
-    }
-  }
+  HostPipe* hp = nullptr;
+  uint64_t off0 = 0, count = 0, chunk = 0, next = 0, k = 0;
   struct Pending {
     bool live = false;
     uint64_t off = 0, n = 0;
   } pend[2];
-  auto retire = [&](int b) -> cudaError_t {
-    if (!pend[b].live) return cudaSuccess;
-    cudaError_t e = cudaEventSynchronize(hp.done[b]);
-    if (e != cudaSuccess) return e;
-    if (!pin_out)
-      std::memcpy(static_cast<char*>(out_host) + pend[b].off * out_stride, hp.stage_out[b], pend[b].n * out_stride);
-    pend[b].live = false;
-    return cudaSuccess;
-  };
-  uint64_t k = 0;
-  for (uint64_t off = 0; off < count; off += chunk, ++k) {
-    const int b = (int)(k & 1);
-    const uint64_t n = count - off < chunk ? count - off : chunk;
-    CK(retire(b), "pipeline wait");
-    const void* t_dev = nullptr;
-    if (!take) {
-      const char* src = static_cast<const char*>(t_host) + off * rs;
-      if (!pin_in) {
-        std::memcpy(hp.stage_in[b], src, n * rs);
-        src = static_cast<const char*>(hp.stage_in[b]);
-      }
-      CK(cudaMemcpyAsync(hp.dev_in[b], src, n * rs, cudaMemcpyHostToDevice, hp.stream[b]), "H2D");
-      t_dev = hp.dev_in[b];
-    }
-    enterp_status es;
-    if (c->core->r.scalar == ENTERP_F32) {
-      auto s = take ? take_src<float>(c->core->r, n_total, first + off, n) : batch_src<float>(t_dev, n);
-      es = dispatch_eval<float>(*c, *rp, s, hp.dev_out[b], hp.stream[b]);
-    } else {
-      auto s = take ? take_src<double>(c->core->r, n_total, first + off, n) : batch_src<double>(t_dev, n);
-      es = dispatch_eval<double>(*c, *rp, s, hp.dev_out[b], hp.stream[b]);
-    }
-    if (es) return es;
-    void* dst = pin_out ? static_cast<void*>(static_cast<char*>(out_host) + off * out_stride) : hp.stage_out[b];
-    CK(cudaMemcpyAsync(dst, hp.dev_out[b], n * out_stride, cudaMemcpyDeviceToHost, hp.stream[b]), "D2H");
-    CK(cudaEventRecord(hp.done[b], hp.stream[b]), "cudaEventRecord");
-    pend[b].live = true;
-    pend[b].off = off;
-    pend[b].n = n;
+};
+
+struct HostJob {
+  enterp_curve* c;
+  bool take;
+  const void* t_host;
+  uint64_t n_total, first;
+  void* out_host;
+  size_t rs, out_stride;
+  bool pin_in, pin_out;
+};
+
+cudaError_t lane_prepare(const HostJob& j, HostLane& l) {
+  HostPipe& hp = *l.hp;
+  cudaError_t e;
+  for (int b = 0; b < 2; ++b) {
+    if (!hp.stream[b] && (e = cudaStreamCreateWithFlags(&hp.stream[b], cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if (!hp.done[b] && (e = cudaEventCreateWithFlags(&hp.done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+    if (!j.take && (e = ensure(hp.dev_in[b], l.chunk * j.rs, false)) != cudaSuccess) return e;
+    if ((e = ensure(hp.dev_out[b], l.chunk * j.out_stride, false)) != cudaSuccess) return e;
+    if (!j.take && !j.pin_in && (e = ensure(hp.stage_in[b], l.chunk * j.rs, true)) != cudaSuccess) return e;
+    if (!j.pin_out && (e = ensure(hp.stage_out[b], l.chunk * j.out_stride, true)) != cudaSuccess) return e;
   }
-  CK(retire(0), "pipeline drain");
-  CK(retire(1), "pipeline drain");
+  return cudaSuccess;
+}
+
+cudaError_t lane_retire(const HostJob& j, HostLane& l, int b) {
+  if (!l.pend[b].live) return cudaSuccess;
+  const cudaError_t e = cudaEventSynchronize(l.hp->done[b]);
+  if (e != cudaSuccess) return e;
+  if (!j.pin_out)
+    std::memcpy(static_cast<char*>(j.out_host) + (l.off0 + l.pend[b].off) * j.out_stride, l.hp->stage_out[b].p,
+                l.pend[b].n * j.out_stride);
+  l.pend[b].live = false;
+  return cudaSuccess;
+}
+
+// Issues the lane's next chunk (H2D of its parameters, kernel, D2H) on the pipe's stream k & 1.
+enterp_status lane_issue(const HostJob& j, HostLane& l) {
+  DeviceGuard g(l.device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  HostPipe& hp = *l.hp;
+  const int b = (int)(l.k & 1);
+  const uint64_t off = l.next;
+  const uint64_t n = l.count - off < l.chunk ? l.count - off : l.chunk;
+  CK(lane_retire(j, l, b), "pipeline wait");
+  const void* t_dev = nullptr;
+  if (!j.take) {
+    const char* src = static_cast<const char*>(j.t_host) + (l.off0 + off) * j.rs;
+    if (!j.pin_in) {
+      std::memcpy(hp.stage_in[b].p, src, n * j.rs);
+      src = static_cast<const char*>(hp.stage_in[b].p);
+    }
+    CK(cudaMemcpyAsync(hp.dev_in[b].p, src, n * j.rs, cudaMemcpyHostToDevice, hp.stream[b]), "H2D");
+    t_dev = hp.dev_in[b].p;
+  }
+  enterp_status es;
+  const Resolved& r = j.c->core->r;
+  if (r.scalar == ENTERP_F32) {
+    auto s = j.take ? take_src<float>(r, j.n_total, j.first + l.off0 + off, n) : batch_src<float>(t_dev, n);
+    es = dispatch_eval<float>(*j.c, *l.rp, s, hp.dev_out[b].p, hp.stream[b]);
+  } else {
+    auto s = j.take ? take_src<double>(r, j.n_total, j.first + l.off0 + off, n) : batch_src<double>(t_dev, n);
+    es = dispatch_eval<double>(*j.c, *l.rp, s, hp.dev_out[b].p, hp.stream[b]);
+  }
+  if (es) return es;
+  void* dst = j.pin_out ? static_cast<void*>(static_cast<char*>(j.out_host) + (l.off0 + off) * j.out_stride) : hp.stage_out[b].p;
+  CK(cudaMemcpyAsync(dst, hp.dev_out[b].p, n * j.out_stride, cudaMemcpyDeviceToHost, hp.stream[b]), "D2H");
+  CK(cudaEventRecord(hp.done[b], hp.stream[b]), "cudaEventRecord");
+  l.pend[b].live = true;
+  l.pend[b].off = off;
+  l.pend[b].n = n;
+  l.next = off + n;
+  ++l.k;
   return ENTERP_OK;
+}
+
+// `Signal::sample(..).collect()` / `Curve::take(n).collect()` with host buffers over one or several GPUs of the box:
+// the sample range is cut into contiguous per-device shares ([g*N/G, (g+1)*N/G), global stepper
+// index), each share runs through its own double-buffered pipe, and ONE host thread issues the chunks round-robin
+// over the devices. Blocks until out_host is complete.
+enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bool take, const void* t_host,
+                          uint64_t n_total, uint64_t first, uint64_t count, void* out_host) {
+  if (!c || !devices || n_devices < 1) return ENTERP_INVALID_ARGUMENT;
+  if (count == 0) return ENTERP_OK;
+  if (!out_host || (!take && !t_host)) return ENTERP_INVALID_ARGUMENT;
+  if (take && (n_total == 0 || first > n_total || count > n_total - first)) return ENTERP_INVALID_ARGUMENT;
+  for (int a = 0; a < n_devices; ++a)
+    for (int b = a + 1; b < n_devices; ++b)
+      if (devices[a] == devices[b]) return ENTERP_INVALID_ARGUMENT;
+  HostJob j{};
+  j.c = c;
+  j.take = take;
+  j.t_host = t_host;
+  j.n_total = n_total;
+  j.first = first;
+  j.out_host = out_host;
+  j.rs = rsize(c->core->r);
+  j.out_stride = j.rs * c->core->r.dim;
+  j.pin_in = take || is_pinned(t_host);
+  j.pin_out = is_pinned(out_host);
+  std::vector<HostLane> lanes((size_t)n_devices);
+  enterp_status st = ENTERP_OK;
+  for (int g = 0; g < n_devices && st == ENTERP_OK; ++g) {
+    HostLane& l = lanes[(size_t)g];
+    l.device = devices[g];
+    const uint64_t lo = (uint64_t)(((unsigned __int128)count * (unsigned)g) / (unsigned)n_devices);
+    const uint64_t hi = (uint64_t)(((unsigned __int128)count * (unsigned)(g + 1)) / (unsigned)n_devices);
+    l.off0 = lo;
+    l.count = hi - lo;
+    l.chunk = l.count < HOST_CHUNK ? l.count : HOST_CHUNK;
+    if (l.count == 0) continue;
+    st = get_replica(c, l.device, &l.rp);
+    if (st) break;
+    DeviceGuard dg(l.device);
+    if (!dg.ok) {
+      st = ENTERP_NO_DEVICE;
+      break;
+    }
+    l.hp = acquire_pipe(l.device);
+    const cudaError_t e = lane_prepare(j, l);
+    if (e != cudaSuccess) st = cuda_fail(e, "host pipeline scratch");
+  }
+  // round-robin issue: every device gets its next chunk before anyone gets a second one
+  bool more = st == ENTERP_OK;
+  while (more) {
+    more = false;
+    for (HostLane& l : lanes) {
+      if (!l.hp || l.next >= l.count) continue;
+      st = lane_issue(j, l);
+      if (st) break;
+      more = more || l.next < l.count;
+    }
+    if (st) break;
+  }
+  // drain (also on errors: nothing may still be writing into the caller's buffers when we return)
+  for (HostLane& l : lanes) {
+    if (!l.hp) continue;
+    DeviceGuard dg(l.device);
+    if (st == ENTERP_OK) {
+      for (int b = 0; b < 2 && st == ENTERP_OK; ++b) {
+        const cudaError_t e = lane_retire(j, l, b);
+        if (e != cudaSuccess) st = cuda_fail(e, "pipeline drain");
+      }
+    }
+    if (st != ENTERP_OK) {
+      for (int b = 0; b < 2; ++b)
+        if (l.hp->stream[b]) cudaStreamSynchronize(l.hp->stream[b]);
+    }
+    release_pipe(l.hp);
+  }
+  return st;
 }
 
 }  // namespace
@@ -719,7 +857,7 @@ ENTERP_API enterp_status enterp_span_take(enterp_curve* c, int device, uint64_t 
 ENTERP_API enterp_status enterp_stepper(int scalar, int device, double start, double end, uint64_t n_total,
                                         uint64_t first, uint64_t count, void* t_out_dev, void* stream) {
   if (count == 0) return ENTERP_OK;
-  if (!t_out_dev || n_total == 0 || first + count > n_total) return ENTERP_INVALID_ARGUMENT;
+  if (!t_out_dev || n_total == 0 || first > n_total || count > n_total - first) return ENTERP_INVALID_ARGUMENT;
   if (scalar != ENTERP_F32 && scalar != ENTERP_F64) return ENTERP_INVALID_ARGUMENT;
   DeviceGuard g(device);
   if (!g.ok) return ENTERP_NO_DEVICE;
@@ -774,7 +912,7 @@ static enterp_status bezier_deriv_common(enterp_curve* c, int device, const void
   // gen_with_deriatives::<K> slices `grad[..=min(K, len-1)]`: out of bounds (a panic upstream) unless K >= len
   if (!tangent && r.n_elem - 1 >= (uint64_t)k) return ENTERP_INVALID_ARGUMENT;
   Replica* rp = nullptr;
-  enterp_status st = get_replica(c, device, &rp);
+  enterp_status st = get_replica(c, device, &rp, static_cast<cudaStream_t>(stream));
   if (st) return st;
   DeviceGuard g(device);
   if (!g.ok) return ENTERP_NO_DEVICE;
@@ -800,13 +938,25 @@ ENTERP_API enterp_status enterp_bezier_derivatives_batch(enterp_curve* c, int de
 }
 
 ENTERP_API enterp_status enterp_sample_host(enterp_curve* c, int device, const void* t_host, uint64_t n, void* out_host) {
-  return host_common(c, device, false, t_host, 0, 0, n, out_host);
+  return host_common(c, &device, 1, false, t_host, 0, 0, n, out_host);
 }
 
 ENTERP_API enterp_status enterp_take_host(enterp_curve* c, int device, uint64_t n_total, uint64_t first, uint64_t count,
                                           void* out_host) {
-  return host_common(c, device, true, nullptr, n_total, first, count, out_host);
+  return host_common(c, &device, 1, true, nullptr, n_total, first, count, out_host);
 }
+
+ENTERP_API enterp_status enterp_sample_host_multi(enterp_curve* c, const int* devices, int n_devices, const void* t_host,
+                                                  uint64_t n, void* out_host) {
+  return host_common(c, devices, n_devices, false, t_host, 0, 0, n, out_host);
+}
+
+ENTERP_API enterp_status enterp_take_host_multi(enterp_curve* c, const int* devices, int n_devices, uint64_t n_total,
+                                                uint64_t first, uint64_t count, void* out_host) {
+  return host_common(c, devices, n_devices, true, nullptr, n_total, first, count, out_host);
+}
+
+ENTERP_API int enterp_host_scratch_release(int device) { return release_idle_pipes(device); }
 
 ENTERP_API enterp_status enterp_host_alloc(void** ptr, uint64_t bytes) {
   if (!ptr) return ENTERP_INVALID_ARGUMENT;
@@ -831,6 +981,30 @@ ENTERP_API enterp_status enterp_invalid_count(enterp_curve* c, int device, unsig
   return ENTERP_OK;
 }
 
+ENTERP_API enterp_status enterp_invalid_count_stream(enterp_curve* c, int device, void* stream, unsigned long long* n) {
+  if (!c || !n) return ENTERP_INVALID_ARGUMENT;
+  Replica* rp = nullptr;
+  enterp_status st = get_replica(c, device, &rp, static_cast<cudaStream_t>(stream));
+  if (st) return st;
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  CK(cudaMemcpyAsync(n, rp->invalid, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs), "cudaMemcpyAsync");
+  CK(cudaStreamSynchronize(cs), "cudaStreamSynchronize");
+  return ENTERP_OK;
+}
+
+ENTERP_API enterp_status enterp_invalid_reset(enterp_curve* c, int device, void* stream) {
+  if (!c) return ENTERP_INVALID_ARGUMENT;
+  Replica* rp = nullptr;
+  enterp_status st = get_replica(c, device, &rp, static_cast<cudaStream_t>(stream));
+  if (st) return st;
+  DeviceGuard g(device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  CK(cudaMemsetAsync(rp->invalid, 0, sizeof(unsigned long long), static_cast<cudaStream_t>(stream)), "cudaMemsetAsync");
+  return ENTERP_OK;
+}
+
 ENTERP_API const char* enterp_status_str(enterp_status s) {
   switch (s) {
     case ENTERP_OK: return "ok";
@@ -847,6 +1021,7 @@ ENTERP_API const char* enterp_status_str(enterp_status s) {
     case ENTERP_UNSUPPORTED: return "unsupported";
     case ENTERP_NO_DEVICE: return "no CUDA device";
     case ENTERP_CUDA_ERROR: return "CUDA error";
+    case ENTERP_NOT_UPLOADED: return "curve not uploaded to this device (call enterp_curve_upload before capturing the stream)";
   }
   return "unknown status";
 }

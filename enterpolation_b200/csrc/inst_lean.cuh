@@ -13,7 +13,7 @@ constexpr unsigned long long LEAN_INDEX_LIMIT = (1ull << 32) - (1ull << 24);  //
 template <class R, bool BATCH>
 bool lean_src(const SampleSrc<R>& s, bool vec_ok, LeanTake<R>& t) {
   if ((s.t != nullptr) != BATCH || !vec_ok || s.count == 0) return false;
-  if (s.first + s.count > LEAN_INDEX_LIMIT) return false;
+  if (s.first > LEAN_INDEX_LIMIT || s.count > LEAN_INDEX_LIMIT - s.first) return false;
   t.step = s.step;
   t.start = s.start;
   t.first = (uint32_t)s.first;

@@ -75,6 +75,7 @@ struct RowsDev {
   R eq_rstep;         // RN(1 / eq_step) (exact when eq_step is a power of two)
   uint32_t ri_off;    // row index = inner index + ri_off (mod 2^32): map_add - lo
   uint32_t pow2_ops;  // exact-division rows: bit t set = factor operation t divides by powers of two in every row
+  uint32_t runs_lt;   // VARIANT 4 (stepper runs): log2 of the index tile a CTA walks at a time (launch-specific)
 };
 
 // ---- exact arithmetic -------------------------------------------------------------------------

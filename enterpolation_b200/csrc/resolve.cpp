@@ -647,7 +647,9 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
   if (d.kind == ENTERP_LINEAR && d.knot_base == ENTERP_KNOTS_SORTED && s.inner_len >= 2) {
     const uint32_t per = 16 / sizeof(R);
     const uint32_t stride = (uint32_t)((2 + 2 * r.dh + per - 1) / per * per);
-    if (stride * sizeof(R) <= 128) {  // up to [f64;4]+weight: 2 knots + 2 x 5 components = 96 bytes
+    // up to [f64;4]+weight: 2 knots + 2 x 5 components = 96 bytes; capped at 256 MiB like the knot rows (beyond that
+    // the kernel gathers knots and elements separately: linear_kernel handles records == nullptr)
+    if (stride * sizeof(R) <= 128 && (s.inner_len - 1) * stride * sizeof(R) <= (1ull << 28)) {
       const R* el = reinterpret_cast<const R*>(r.elems.data());
       std::vector<R> rec((size_t)(s.inner_len - 1) * stride, R(0));
       for (uint64_t j = 0; j + 1 < s.inner_len; ++j) {

@@ -210,7 +210,7 @@ constexpr int ROWS_S = 2;  // samples per thread per loop trip (block-strided, s
 // rarely, row reloads can come from global memory / L2 (tables of any size), and the span computation (sorted
 // knots: the pivot search; equidistant: the exact division and floor) is skipped while the parameter stays inside
 // the cached row's [hold_lo, hold_hi) interval, which the host tabulated with the kernel's own arithmetic.
-template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, bool TAKE, bool CHECK, bool CHUNK>
+template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, bool TAKE, bool CHECK, bool CHUNK, bool RUNS = false>
 __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<R>& s, R* __restrict__ out,
                                           const RowsDev<R>& rw, const R* __restrict__ tab) {
   using P = PK<R>;
@@ -236,6 +236,10 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
     stride = TILE;
     block0 = t0 * TILE;
     rest = (t1 * TILE < s.count ? t1 * TILE : s.count) - block0;
+  } else if (RUNS) {
+    stride = TILE;  // unused: the run walk below has its own decomposition
+    block0 = 0;
+    rest = 0;
   } else {
     stride = (unsigned long long)gridDim.x * TILE;
     block0 = (unsigned long long)blockIdx.x * TILE;
@@ -256,7 +260,7 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
   const T one2 = P::bcast(rw.one);
 
   // de Boor for one sample whose span row index is ri (bspline/mod.rs:156-168)
-  auto eval_one = [&](const R x, const bool valid, const uint32_t ri, R* __restrict__ dst) {
+  auto eval_to = [&](const R x, const bool valid, const uint32_t ri, auto&& sink) {
     if (ri != cached) {
       const float4* __restrict__ src = reinterpret_cast<const float4*>(tab + (size_t)ri * ROW);
 #pragma unroll
@@ -350,7 +354,10 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
       for (int q = 0; q < D; ++q) v[q] = qnan(R(0));
       atomicAdd(c.invalid, 1ull);
     }
-    store_elem<R, D>(dst, 0, v, true);
+    sink(v);
+  };
+  auto eval_one = [&](const R x, const bool valid, const uint32_t ri, R* __restrict__ dst) {
+    eval_to(x, valid, ri, [&](const R(&v)[D]) { store_elem<R, D>(dst, 0, v, true); });
   };
 
   // Input adaptors (Clamp / Slice / Bezier-style affine maps, base/adaptors.rs) ride on the CHECK variant
@@ -382,6 +389,79 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
     }
     return x;
   };
+
+  // RUNS (f32 take() beyond index 2^24): the stepper's fl(i) (Equidistant::eval, list.rs:416-418: `step *
+  // R::from_usize(i) + offset`) has a 24-bit mantissa, so from 2^24 on consecutive indices share their parameter in
+  // runs of 2^(floor(log2 i) - 23) samples (256 in the upper half of a take(2^32)) and the reference evaluates the
+  // same t over and over. Here a CTA walks tiles of 2^lt consecutive indices; per sub-tile it evaluates each DISTINCT
+  // parameter once (thread m takes the m-th representable index v = vb + m * 2^ls, exactly a float), parks the
+  // results in shared memory, and then all threads stream the samples out: sample i reads the value of
+  // RN-even(i / 2^ls), which is what from_usize(i) rounds to, computed in integers. Bit-exact by construction
+  // (same t, same arithmetic), ~1/2^ls of the FP work, and the kernel runs at the store roof.
+  if constexpr (RUNS) {
+    static_assert(sizeof(R) == 4 && TAKE && !CHECK && !CHUNK, "f32 check-free take only");
+    constexpr int NV = BLOCK;
+    __shared__ __align__(16) R vals[2][(NV + 1) * D];
+    const unsigned lt = rw.runs_lt;
+    const unsigned long long A = s.first, B = s.first + s.count;
+    const unsigned long long tile1 = (B - 1) >> lt;
+    int buf = 0;
+    for (unsigned long long tile = (A >> lt) + blockIdx.x; tile <= tile1; tile += gridDim.x) {
+      const unsigned long long base = tile << lt;            // >= 2^24 (host), a multiple of 2^lt
+      const int ls = 40 - __clzll((long long)base);          // floor(log2 base) - 23 >= 1: fl() spacing of the binade
+      const unsigned long long T = 1ull << lt;
+      const unsigned long long SUB = (ls >= (int)lt || ((unsigned long long)NV << ls) > T) ? T : ((unsigned long long)NV << ls);
+      for (unsigned long long sb = base; sb < base + T; sb += SUB) {
+        if (sb >= B || sb + SUB <= A) continue;              // uniform: nothing of the launch in this sub-tile
+        const unsigned long long vb = (sb >> ls) << ls;      // representable index at or below the sub-tile
+        const uint32_t nvals = (uint32_t)((sb + SUB - 1 - vb) >> ls) + 2u;  // <= NV + 1
+        R* __restrict__ vbuf = vals[buf];
+        for (uint32_t m = threadIdx.x; m < nvals; m += BLOCK) {
+          const unsigned long long v = vb + ((unsigned long long)m << ls);
+          const R x = xadd(xmul(s.step, from_index(v, R(0))), s.start);  // from_index(v) is exact
+          bool valid;
+          const uint32_t ri = rows_span<R, EQUI, POW2, false>(c, rw, x, valid);
+          eval_to(x, true, ri, [&](const R(&v4)[D]) {
+#pragma unroll
+            for (int q = 0; q < D; ++q) vbuf[m * D + q] = v4[q];
+          });
+        }
+        __syncthreads();  // one barrier per sub-tile: the other buffer is free once everybody has passed this one
+        const unsigned long long lo_i = sb > A ? sb : A;
+        const unsigned long long hi_i = sb + SUB < B ? sb + SUB : B;
+        // m(i) = RN-even((i - vb) / 2^ls) = (dd + 2^(ls-1) - 1 + parity) >> ls with parity = bit 0 of the truncated
+        // quotient i >> ls (the mantissa from_usize would keep): branch-free, 32-bit unless the run length is huge.
+        auto stream_out = [&](auto zero) {
+          using U = decltype(zero);
+          const U hm1 = (U)(((1ull << ls) >> 1) - 1ull);
+          const U vpar = (U)((vb >> ls) & 1ull);
+          U dd = (U)(lo_i - vb) + (U)threadIdx.x;
+          const U end = (U)(hi_i - vb);
+          R* __restrict__ dst = out + (lo_i - A + threadIdx.x) * D;
+#pragma unroll 4
+          for (; dd < end; dd += (U)BLOCK, dst += (size_t)BLOCK * D) {
+            const U par = ((dd >> ls) + vpar) & (U)1;
+            const uint32_t m = (uint32_t)((dd + hm1 + par) >> ls);
+            R v4[D];
+            if constexpr (D == 4) {
+              const float4 t4 = reinterpret_cast<const float4*>(vbuf)[m];
+              v4[0] = t4.x; v4[1] = t4.y; v4[2] = t4.z; v4[3] = t4.w;
+            } else if constexpr (D == 2) {
+              const float2 t2 = reinterpret_cast<const float2*>(vbuf)[m];
+              v4[0] = t2.x; v4[1] = t2.y;
+            } else {
+#pragma unroll
+              for (int q = 0; q < D; ++q) v4[q] = vbuf[m * D + q];
+            }
+            store_elem<R, D>(dst, 0, v4, true);
+          }
+        };
+        if (ls <= 20) stream_out(uint32_t(0)); else stream_out((unsigned long long)0);
+        buf ^= 1;
+      }
+    }
+    return;
+  }
 
   // Batches: the parameters of the NEXT trip are requested before this trip's arithmetic, so their DRAM latency
   // hides behind ~130 instructions of de Boor instead of stalling the head of every trip.
@@ -444,14 +524,17 @@ __host__ __device__ constexpr int rows_min_blocks(int P, int DH, bool POW2) {
 // make the reference panic: t_i = step*fl(i)+start is monotone in i and the set of parameters the
 // reference accepts is an interval unbounded below, so it suffices that both ends of the launch's range
 // are valid), 3 = take, check-free, CHUNKed, rows read from global memory (any table size; sorted knots skip
-// the search while a thread stays in its span). Separate kernels rather than paths in one: the hot loop is
-// I-cache sensitive.
+// the search while a thread stays in its span), 4 = f32 take beyond index 2^24, check-free: one evaluation per
+// distinct stepper value, broadcast through shared memory (RUNS above). Separate kernels rather than paths in one:
+// the hot loop is I-cache sensitive.
 template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, int VARIANT>
 __global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH, POW2)) bspline_rows_kernel(const CurveDev<R> c,
                                                                                                const SampleSrc<R> s,
                                                                                                R* __restrict__ out,
                                                                                                const RowsDev<R> rw) {
-  if constexpr (VARIANT == 3) {
+  if constexpr (VARIANT == 4) {
+    rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, false, false, true>(c, s, out, rw, rw.table);
+  } else if constexpr (VARIANT == 3) {
     rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, false, true>(c, s, out, rw, rw.table);
   } else if constexpr (VARIANT == 1) {
     rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, true, true>(c, s, out, rw, rw.table);

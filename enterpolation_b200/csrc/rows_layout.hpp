@@ -8,7 +8,14 @@
 
 namespace enterp {
 
-constexpr int ROWS_MAX_DEGREE = 7;
+// Highest degree with span-row kernels. The default build instantiates degrees 1..4 (what the reference's examples,
+// benches and BASELINE.json's configs use); `make ROWS_MAX_DEGREE=7` adds 5..7 (they triple the size of the rows
+// translation units). Above the limit B-splines run through the generic kernel (compile-time degree up to 7).
+#ifndef ENTERP_ROWS_MAX_DEGREE
+#define ENTERP_ROWS_MAX_DEGREE 4
+#endif
+constexpr int ROWS_MAX_DEGREE = ENTERP_ROWS_MAX_DEGREE;
+static_assert(ROWS_MAX_DEGREE >= 1 && ROWS_MAX_DEGREE <= 7, "span rows exist for degrees 1..7");
 constexpr unsigned ROWS_MAX_BYTES = 64u * 1024u;  // shared-memory budget of the row table per CTA
 // Bigger tables stay in global memory and serve take() only (chunked kernel variant: a CTA walks a contiguous
 // sample range, so a thread's span changes rarely and the row reloads come out of L2).

@@ -21,6 +21,8 @@ def _check(lib, status: int):
         return
     if status in (_abi.NO_DEVICE, _abi.CUDA_ERROR):
         raise DeviceError(f"{lib.enterp_status_str(status).decode()}: {lib.enterp_last_cuda_error().decode()}")
+    if status == _abi.NOT_UPLOADED:
+        raise DeviceError(lib.enterp_status_str(status).decode())
     info = _abi.ErrorInfo()
     info.status = status
     raise from_info(info)
@@ -108,13 +110,19 @@ class Curve:
         out = self.sample([t])
         return out[0]
 
-    def sample(self, ts, device: int | None = None):
-        """`Signal::sample(iter).collect()`: host parameters in, host elements out (numpy)."""
+    def sample(self, ts, device: int | None = None, devices=None):
+        """`Signal::sample(iter).collect()`: host parameters in, host elements out (numpy). `devices=[..]` spreads
+        the batch over several GPUs of the box with one call (enterp_sample_host_multi)."""
         dev = self.device if device is None else device
         t = np.ascontiguousarray(np.asarray(ts, dtype=self.dtype)).reshape(-1)
         out = np.empty((t.shape[0], self.dim), dtype=self.dtype)
         if t.shape[0]:
-            _check(self._lib, self._lib.enterp_sample_host(self._h, dev, t.ctypes.data, t.shape[0], out.ctypes.data))
+            if devices is not None:
+                arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+                st = self._lib.enterp_sample_host_multi(self._h, arr, len(devices), t.ctypes.data, t.shape[0], out.ctypes.data)
+            else:
+                st = self._lib.enterp_sample_host(self._h, dev, t.ctypes.data, t.shape[0], out.ctypes.data)
+            _check(self._lib, st)
         return out.reshape(-1) if self.dim == 1 else out
 
     extract = sample
@@ -201,12 +209,21 @@ class Curve:
         _check(self._lib, st)
         return out.cpu().numpy() if host else out
 
-    def invalid_count(self, device=None) -> int:
-        """How many samples so far would have made the reference panic (written as NaN)."""
+    def invalid_count(self, device=None, stream=None) -> int:
+        """How many samples so far would have made the reference panic (written as NaN). With `stream` only that
+        stream is synchronised (enterp_invalid_count_stream); otherwise the whole device."""
         dev = self.device if device is None else device
         n = C.c_ulonglong(0)
-        _check(self._lib, self._lib.enterp_invalid_count(self._h, dev, C.byref(n)))
+        if stream is not None:
+            _check(self._lib, self._lib.enterp_invalid_count_stream(self._h, dev, _stream_ptr(stream), C.byref(n)))
+        else:
+            _check(self._lib, self._lib.enterp_invalid_count(self._h, dev, C.byref(n)))
         return int(n.value)
+
+    def invalid_reset(self, device=None, stream=None):
+        """Zero the counter in stream order, so that reset -> eval -> invalid_count(stream=..) belongs to one call."""
+        dev = self.device if device is None else device
+        _check(self._lib, self._lib.enterp_invalid_reset(self._h, dev, _stream_ptr(stream)))
 
 
 class Take:
@@ -232,12 +249,18 @@ class Take:
         lo, hi = shard_range(self.samples, rank, world)
         return Take(self.curve, self.samples, lo, hi - lo)
 
-    def collect(self, device: int | None = None) -> np.ndarray:
+    def collect(self, device: int | None = None, devices=None) -> np.ndarray:
+        """`take(n).collect()`; `devices=[..]`: one call sharded over several GPUs (enterp_take_host_multi)."""
         c = self.curve
         dev = c.device if device is None else device
         out = np.empty((self.count, c.dim), dtype=c.dtype)
         if self.count:
-            _check(c._lib, c._lib.enterp_take_host(c._h, dev, self.samples, self.first, self.count, out.ctypes.data))
+            if devices is not None:
+                arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+                st = c._lib.enterp_take_host_multi(c._h, arr, len(devices), self.samples, self.first, self.count, out.ctypes.data)
+            else:
+                st = c._lib.enterp_take_host(c._h, dev, self.samples, self.first, self.count, out.ctypes.data)
+            _check(c._lib, st)
         return out.reshape(-1) if c.dim == 1 else out
 
     def collect_device(self, device: int | None = None, out=None, stream=None):

@@ -63,7 +63,10 @@ typedef enum enterp_status {
   ENTERP_INVALID_ARGUMENT = 10,           /* malformed descriptor / NULL pointer / bad enum */
   ENTERP_UNSUPPORTED = 11,                /* combination the reference has no impl block for */
   ENTERP_NO_DEVICE = 12,                  /* no CUDA device / device index out of range */
-  ENTERP_CUDA_ERROR = 13                  /* a CUDA runtime call failed; see enterp_last_cuda_error */
+  ENTERP_CUDA_ERROR = 13,                 /* a CUDA runtime call failed; see enterp_last_cuda_error */
+  ENTERP_NOT_UPLOADED = 14                /* first use of the curve on this device while `stream` is being captured into a
+                                             CUDA graph: the one-time table upload cannot run inside a capture; call
+                                             enterp_curve_upload(curve, device) first */
 } enterp_status;
 
 enum { ENTERP_LINEAR = 0, ENTERP_BEZIER = 1, ENTERP_BSPLINE = 2 };           /* desc.kind      */
@@ -234,15 +237,34 @@ ENTERP_API enterp_status enterp_sample_host(enterp_curve* curve, int device, con
 /* `curve.take(n_total).skip(first).take(count).collect()`. */
 ENTERP_API enterp_status enterp_take_host(enterp_curve* curve, int device, uint64_t n_total,
                                           uint64_t first, uint64_t count, void* out_host);
-/* Pinned host memory for zero-staging transfers of the two calls above. */
+/* The same two calls spread over several GPUs of the box by ONE call from one host thread: the sample
+ * range is cut into n_devices contiguous shares (share g = [g*count/n, (g+1)*count/n), evaluated with the GLOBAL
+ * stepper index so the result equals the single-device call bit for bit), every device keeps a replica of the curve
+ * (uploaded on first use) and runs its own double-buffered kernel/D2H pipeline; chunks are issued round-robin. No
+ * collective is involved. `devices` must not repeat an ordinal. */
+ENTERP_API enterp_status enterp_sample_host_multi(enterp_curve* curve, const int* devices, int n_devices,
+                                                  const void* t_host, uint64_t n, void* out_host);
+ENTERP_API enterp_status enterp_take_host_multi(enterp_curve* curve, const int* devices, int n_devices,
+                                                uint64_t n_total, uint64_t first, uint64_t count, void* out_host);
+/* The host-buffer calls borrow pooled scratch (2 device chunk buffers, 2 streams, optional pinned staging) that is
+ * kept for the next call. This frees every idle pipe of `device` (all devices when device < 0); returns the count. */
+ENTERP_API int enterp_host_scratch_release(int device);
+/* Pinned host memory for zero-staging transfers of the calls above. */
 ENTERP_API enterp_status enterp_host_alloc(void** ptr, uint64_t bytes);
 ENTERP_API void enterp_host_free(void* ptr);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 
-/* Number of samples so far (on `device`) for which the reference would have panicked. */
+/* Number of samples so far (on `device`) for which the reference would have panicked. NOTE: the eval entry points
+ * return ENTERP_OK even when samples were invalid (they come back as NaN); the counter is cumulative per device
+ * replica and shared by the handles derived from one curve (clamp / slice). enterp_invalid_count synchronises the
+ * whole device; the _stream form only `stream`, and enterp_invalid_reset zeroes the counter in stream order, so
+ * reset -> eval -> count_stream on one stream attributes invalid samples to one call. */
 ENTERP_API enterp_status enterp_invalid_count(enterp_curve* curve, int device,
                                               unsigned long long* n);
+ENTERP_API enterp_status enterp_invalid_count_stream(enterp_curve* curve, int device, void* stream,
+                                                     unsigned long long* n);
+ENTERP_API enterp_status enterp_invalid_reset(enterp_curve* curve, int device, void* stream);
 ENTERP_API const char* enterp_status_str(enterp_status status);
 ENTERP_API const char* enterp_last_cuda_error(void);
 ENTERP_API int enterp_device_count(void);

@@ -758,3 +758,122 @@ def test_hold_intervals_at_every_float_around_the_knots(scalar, knots_kind):
         for k in knots[1:-1]:
             first = int(round((float(k) - float(d[0])) / step)) - 2048
             assert_bits_equal(lc.take_device(n_total, first, 4096).cpu().numpy(), lr.take(n_total, first, 4096), f"linear window on {k}")
+
+
+# ---- f32 stepper runs (rows.cuh RUNS / VARIANT 4): from index 2^24 on, from_usize(i) repeats in runs ------------------
+def _runs_builders():
+    el4 = rand_elements(5, 4, np.float32, 0x51)
+    yield "C5 5 stops", BSpline.builder().clamped().elements(el4).equidistant("f32").degree(3).normalized().dynamic()
+    el256 = rand_elements(256, 4, np.float32, 0x52)
+    yield "C5 256 stops", BSpline.builder().clamped().elements(el256).equidistant("f32").degree(3).normalized().dynamic()
+    for dim in (1, 2, 3):
+        el = rand_elements(23, dim, np.float32, 0x53 + dim)
+        yield f"sorted quadratic dim {dim}", BSpline.builder().elements(el).knots(sorted_knots(24, np.float32, 0x54)).constant(3)
+    pts = rand_elements(40, 3, np.float32, 0x58)
+    w = (u01(40, 0x59, np.float32) + np.float32(0.5)).astype(np.float32)
+    yield "nurbs", BSpline.builder().elements_with_weights(pts, w).knots(sorted_knots(42, np.float32, 0x5A)).constant(4)
+
+
+@pytest.mark.parametrize("name,builder", list(_runs_builders()), ids=lambda v: v if isinstance(v, str) else "")
+def test_take_f32_stepper_runs(name, builder):
+    curve = builder.build()
+    ref = oracle.OracleCurve(builder.to_desc())
+    lib = _abi.load_library()
+    cases = []
+    n32 = 1 << 32
+    for k in range(24, 32):  # run-length changes: 2^k - 300 .. 2^k + 300 (and odd, unaligned windows)
+        cases.append((n32, (1 << k) - 300, 601))
+        cases.append((n32, (1 << k) - 4097 - k, 9001))
+    cases += [(n32, (1 << 24) - 70000, 200001),      # head below 2^24 + tail above in one call
+              (n32, n32 - 100000, 100000),           # the end of the take (fl(i) rounds up to 2^32)
+              (n32 - 12345, 3 * (1 << 29) + 17, 70001),
+              ((1 << 25) + 5, 0, (1 << 25) + 5),     # a whole take that crosses 2^24
+              ((1 << 40) + 3, (1 << 39) + 12345, 150000),   # runs longer than a tile
+              ((1 << 40) + 3, (1 << 37) - 4000, 150000)]
+    for n_total, first, count in cases:
+        before = lib.enterp_launch_count()
+        got = curve.take_device(n_total, first, count).cpu().numpy()
+        assert lib.enterp_launch_count() - before in (1, 2)
+        assert_bits_equal(got, ref.take(n_total, first, count), f"{name} take({n_total}) [{first}, +{count})")
+
+
+# ---- host-buffer calls over several devices, scratch pool, counters, capture guard ------------------------------------
+def test_take_and_sample_host_multi_device():
+    """enterp_take_host_multi / enterp_sample_host_multi: ONE call from one host thread shards the range over every GPU
+    of the box (contiguous shares, global stepper index): equal to the single-device call and to the oracle."""
+    n_dev = torch.cuda.device_count()
+    devices = list(range(n_dev))
+    b = _c5_like("f32", 9, 4)
+    curve = b.build()
+    ref = oracle.OracleCurve(b.to_desc())
+    n_total, first, count = (1 << 26) + 11, (1 << 24) - 1000, (1 << 23) + 12345  # several chunks per device, crosses 2^24
+    from enterpolation_b200.curve import Take
+    got = Take(curve, n_total, first, count).collect(devices=devices)
+    assert_bits_equal(got, ref.take(n_total, first, count, threads=8), f"take_host_multi over {n_dev} device(s)")
+    one = Take(curve, n_total, first, count).collect()
+    assert_bits_equal(got, one, "multi == single")
+    lin_b = Linear.builder().elements(rand_elements(300, 3, np.float64, 0xD1)).knots(sorted_knots(300, np.float64, 0xD2))
+    lin = lin_b.build()
+    t = (u01((1 << 22) + 77, 0xD3, np.float64) * 200.0 - 10.0)
+    assert_bits_equal(lin.sample(t, devices=devices), oracle.OracleCurve(lin_b.to_desc()).eval(t, threads=8), "sample_host_multi")
+    lib = _abi.load_library()
+    import ctypes as C
+    arr = (C.c_int * 2)(0, 0)
+    out = np.empty((16, 4), dtype=np.float32)
+    assert lib.enterp_take_host_multi(curve._h, arr, 2, 16, 0, 16, out.ctypes.data) == _abi.INVALID_ARGUMENT  # repeated ordinal
+    assert lib.enterp_take_host_multi(curve._h, arr, 1, 16, 2 ** 64 - 1, 2, out.ctypes.data) == _abi.INVALID_ARGUMENT  # wraps
+    assert lib.enterp_host_scratch_release(-1) >= 1  # the idle pipes of the calls above
+    assert_bits_equal(Take(curve, 99).collect(devices=devices), ref.take(99), "after scratch release")
+
+
+def test_range_checks_do_not_wrap():
+    curve = _c5_like("f32", 5, 4).build()
+    out = torch.empty((8, 4), dtype=torch.float32, device="cuda")
+    lib = _abi.load_library()
+    big = 2 ** 64 - 1
+    assert lib.enterp_eval_take(curve._h, 0, 1000, big, 2, out.data_ptr(), None) == _abi.INVALID_ARGUMENT
+    assert lib.enterp_eval_take(curve._h, 0, 1000, 999, 2, out.data_ptr(), None) == _abi.INVALID_ARGUMENT
+    assert lib.enterp_span_take(curve._h, 0, 1000, big, 2, out.data_ptr(), None, None) == _abi.INVALID_ARGUMENT
+    assert lib.enterp_stepper(_abi.F32, 0, 0.0, 1.0, 1000, big, 2, out.data_ptr(), None) == _abi.INVALID_ARGUMENT
+    assert lib.enterp_eval_take(curve._h, 0, 1000, 999, 1, out.data_ptr(), None) == _abi.OK
+
+
+def test_invalid_counter_reset_and_stream_scope():
+    b = BSpline.builder().clamped().elements(rand_elements(7, 2, np.float32, 0xD5)).equidistant("f32").degree(3).domain(0.0, 3.0).dynamic()
+    curve = b.build()
+    s = torch.cuda.Stream()
+    t = torch.tensor([0.5, float("nan"), 1.5, float("inf"), 2.0, float("nan")], dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    curve.sample_device(t, stream=s)
+    assert curve.invalid_count(stream=s) == 3
+    curve.invalid_reset(stream=s)
+    assert curve.invalid_count(stream=s) == 0
+    curve.sample_device(t[:3], stream=s)
+    assert curve.invalid_count(stream=s) == 1
+    assert curve.invalid_count() == 1
+
+
+def test_first_use_inside_a_capture_is_reported():
+    """The one-time upload cannot run while the caller's stream is being captured: ENTERP_NOT_UPLOADED, the capture
+    survives, and after enterp_curve_upload the same call captures fine."""
+    from enterpolation_b200 import DeviceError
+    b = _c5_like("f32", 6, 4)
+    curve = b.build()
+    n = 1000
+    out = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        g.capture_begin()
+        with pytest.raises(DeviceError):
+            curve.take_device(n, out=out, stream=s)
+        g.capture_end()
+    curve.upload(0)
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        g2.capture_begin()
+        curve.take_device(n, out=out, stream=s)
+        g2.capture_end()
+    g2.replay()
+    torch.cuda.synchronize()
+    assert_bits_equal(out.cpu().numpy(), oracle.OracleCurve(b.to_desc()).take(n), "captured after upload")
