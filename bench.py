@@ -30,13 +30,16 @@ if ROOT not in sys.path:
 METRIC = "curve samples/sec"
 UNIT = "samples/s"
 
-# FP-pipe issue peaks measured on this pool's B200 with tools/pipebench.cu (profiles/r01_pipebench.json):
-# dependency-free unfused FMUL/FADD chains, whole chip, lane-operations per second.
+# FP-pipe issue peaks, lane-operations per second, both stated: MEASURED on this pool's B200 with
+# tools/pipebench.cu (profiles/r01_pipebench.json: dependency-free unfused FMUL/FADD chains, whole chip, clocks
+# settle at ~1.82 GHz under that load) and THEORETICAL = 148 SMs x 128 (64) lanes x 1.965 GHz (max SM clock).
 FP32_LANE_OPS = 3.45e13
-# ncu --set full, bspline_rows_kernel<float,4,0,3,1,1,2>, 2^30-sample launch: (17.120574e9 + 250.88e3) B / 2^30 samples
-NCU_C5_DRAM_BYTES_PER_SAMPLE = (17.120574e9 + 250.88e3) / (1 << 30)
 FP64_LANE_OPS = 1.80e13
-
+FP32_LANE_OPS_THEORETICAL = 148 * 128 * 1.965e9
+FP64_LANE_OPS_THEORETICAL = 148 * 64 * 1.965e9
+# ncu --set full of the stepper-run kernel bspline_rows_kernel<float,4,0,3,1,1,4> on a 2^30-sample launch
+# (profiles/r02_ncu_c5_runs.txt): (dram__bytes_write.sum + dram__bytes_read.sum) / samples
+NCU_C5_DRAM_BYTES_PER_SAMPLE = 16.0
 
 # ---- deterministic synthetic inputs: splitmix64(seed + index) ----------------------
 def splitmix64(idx, seed):
@@ -80,6 +83,17 @@ def u01_torch(n, seed, dtype, device, offset=0):
     return out
 
 
+def best_rate(fn, n, reps=3):
+    """samples/s of fn(): one untimed warm-up, then the best of `reps` timed runs."""
+    fn()
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return n / best
+
+
 # ---- workloads ------------------------------------------------------------------------------------
 class Workload:
     """One BASELINE.json config, sharded for (rank, world). Subclasses build device state in setup()."""
@@ -109,7 +123,7 @@ class Workload:
 
 def gradient_builder(stops: int):
     from enterpolation_b200 import BSpline
-    el = u01(stops * 4, 0xE1, np.float32).reshape(stops, 4)
+    el = gradient_elements(stops)
     return BSpline.builder().clamped().elements(el).equidistant("f32").degree(3).normalized().dynamic()
 
 
@@ -141,14 +155,16 @@ class TakeWorkload(Workload):
         ref = oracle.OracleCurve(self.builder.to_desc())
         n = min(n, self.n_total)
         first = (self.n_total - n) // 2
-        t0 = time.perf_counter()
-        ref.take(self.n_total, first, n, threads=threads)
-        return n / (time.perf_counter() - t0)
+        out = np.zeros((n, self.dim), dtype=ref.dtype)  # pre-touched: no first-touch page faults inside the timing
+        return best_rate(lambda: ref.take(self.n_total, first, n, threads=threads, out=out), n)
 
 
 class C5(TakeWorkload):
     key = "C5"
-    kernel = "bspline_rows_kernel<float,4,false,3,true,POW2>"
+    # VARIANT 4 = stepper runs (rows.cuh RUNS): beyond index 2^24 an f32 take repeats its parameter in runs; every
+    # distinct parameter is evaluated once and the samples are streamed out of shared memory. The 2^24-sample head
+    # runs the per-sample variant 2 (5 stops) / 3 (more stops).
+    kernel = "bspline_rows_kernel<float,4,false,3,true,POW2,4>"
     bytes_per_sample = 16
     fp_ops_per_sample = 125
 
@@ -156,8 +172,7 @@ class C5(TakeWorkload):
         import torch
         super().__init__(gradient_builder(stops), log2n, 4, torch.float32, **kw)
         self.stops = stops
-        self.name = (f"C5 dynamic clamped equidistant cubic BSpline [f32;4], {stops} stops, take(2^{log2n}) "
-                     f"sharded over ranks by contiguous global sample range")
+        self.name = c5_name(log2n, stops)
 
 
 class C1(TakeWorkload):
@@ -209,9 +224,8 @@ class BatchWorkload(Workload):
         ref = oracle.OracleCurve(self.builder.to_desc())
         n = min(n, self.samples)
         t = self.t[:n].cpu().numpy()
-        t0 = time.perf_counter()
-        ref.eval(t, threads=threads)
-        return n / (time.perf_counter() - t0)
+        out = np.zeros((n, self.dim), dtype=ref.dtype)
+        return best_rate(lambda: ref.eval(t, threads=threads, out=out), n)
 
 
 class C2(BatchWorkload):
@@ -298,9 +312,7 @@ class C3(Workload):
         from oracle import oracle
         curves = max(threads, min(self.curves, n // self.per_curve))
         ctrl = self.ctrl[:curves].cpu().numpy()
-        t0 = time.perf_counter()
-        oracle.bezier_many_take(ctrl, self.per_curve, threads=threads)
-        return curves * self.per_curve / (time.perf_counter() - t0)
+        return best_rate(lambda: oracle.bezier_many_take(ctrl, self.per_curve, threads=threads), curves * self.per_curve)
 
 
 def make_workload(case, log2n=None, arg=None, rank=0, world=1, device=0):
@@ -382,34 +394,95 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+# ---- shared by both arms -----------------------------------------------------------------------------
+def c5_name(log2n, stops):
+    return (f"C5 dynamic clamped equidistant cubic BSpline [f32;4], {stops} stops, take(2^{log2n}) "
+            f"sharded over ranks by contiguous global sample range")
+
+
+def headline_config(args):
+    """The `config` object of the JSON line: identical in both arms (--impl b200 / reference)."""
+    return {"workload": c5_name(args.log2_samples, args.stops), "samples_total": 1 << args.log2_samples,
+            "elements": f"[f32;4] x {args.stops}", "n_gpus": args.gpus,
+            "l2_policy": "outputs (16 B/sample, 64 GiB / n_gpus per rank at 2^32) are larger than L2; nothing is re-read",
+            "parity": "bit-exact vs CPU oracle (tests/test_gpu_parity.py, tests/test_gpu_fullsize.py)"}
+
+
+def gradient_elements(stops):
+    return u01(stops * 4, 0xE1, np.float32).reshape(stops, 4)
+
+
+def oracle_gradient(stops):
+    """The C5 curve built for the CPU oracle WITHOUT importing the product package (oracle/desc.py)."""
+    from oracle import desc, oracle
+    d = desc.bspline(gradient_elements(stops), desc.F32, mode=desc.CLAMPED,
+                     equidistant=(desc.EQ_BY_DEGREE, 3, desc.EQ_NORMALIZED, 0.0, 0.0), space=(desc.SPACE_DYNAMIC, 0))
+    return oracle.OracleCurve(d)
+
+
+README_ELEMENTS = [
+    943.0, 978.0, 579.0, 15.0, 608.0, 938.0, 669.0, 98.0, 720.0, 303.0, 345.0, 421.0, 767.0, 798.0, 379.0, 379.0, 794.0,
+    774.0, 559.0, 315.0, 141.0, 465.0, 721.0, 398.0, 265.0, 921.0, 664.0, 701.0, 433.0, 494.0, 286.0, 331.0, 976.0, 493.0,
+    296.0, 93.0, 963.0, 422.0, 398.0, 358.0, 906.0, 80.0, 272.0, 287.0, 867.0, 995.0, 109.0, 874.0, 840.0, 931.0, 554.0,
+    405.0, 643.0, 820.0, 229.0, 736.0, 117.0, 317.0, 105.0, 168.0, 16.0, 267.0, 481.0, 547.0, 308.0, 463.0, 664.0, 948.0,
+    655.0, 201.0, 439.0, 910.0, 431.0, 945.0, 441.0, 682.0, 272.0, 716.0, 851.0, 916.0, 98.0, 162.0, 536.0, 129.0, 369.0,
+    753.0, 735.0, 511.0, 346.0, 137.0, 221.0, 715.0, 565.0, 305.0, 649.0, 913.0, 215.0, 713.0, 321.0, 95.0]
+
+
+def readme_anchor():
+    """The reference's only published timing (README.md:133, benches/benches.rs:5-27, 62-93): a degree-3 B-spline
+    over 100 f64 elements, `take(200).collect()`, in its dynamic / constant / uniform flavours. Timed through the
+    CPU oracle, single thread, per-iteration output allocation like criterion's `b.iter::<Vec<f64>, _>`; it anchors
+    the CPU denominators of this bench to the crate's own numbers (other hardware, rustc instead of g++ -O2)."""
+    from oracle import desc, oracle
+    knots = [0.0, 0.0] + [float(i) for i in range(98)] + [97.0, 97.0]
+    assert len(knots) == 102 and len(README_ELEMENTS) == 100
+    curves = {
+        "dynamic": desc.bspline(README_ELEMENTS, desc.F64, knots=knots, space=(desc.SPACE_DYNAMIC, 0)),
+        "constant": desc.bspline(README_ELEMENTS, desc.F64, knots=knots, space=(desc.SPACE_CONSTANT, 4)),
+        "uniform": desc.bspline(README_ELEMENTS, desc.F64, equidistant=(desc.EQ_BY_DEGREE, 3, desc.EQ_NORMALIZED, 0.0, 0.0),
+                                space=(desc.SPACE_CONSTANT, 4)),
+    }
+    published = {"dynamic": 23.160e3 / 200, "constant": 6.6834e3 / 200, "uniform": 9.9186e3 / 200}
+    out = {"shape": "BSpline degree 3, 100 f64 elements, take(200).collect(), single thread (benches/benches.rs:5-27, 62-93)",
+           "unit": "ns/sample", "published_source": "README.md:133 (other hardware, rustc)"}
+    for name, d in curves.items():
+        ref = oracle.OracleCurve(d)
+        ref.bench_take(200, 2000)
+        best = min(ref.bench_take(200, 20000) for _ in range(3))
+        out[name] = {"oracle_ns_per_sample": best / (200 * 20000) * 1e9, "published_ns_per_sample": published[name]}
+    return out
+
+
 # ---- the reference arm --------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's CPU path (C++ restatement in oracle/; the Rust crate cannot be
-    built here: no cargo/rustc in the image) with all host threads, bounded sample per step."""
+    built here: no cargo/rustc in the image) with all host threads, bounded sample per step. Does not import the
+    product package (the descriptor is built by oracle/desc.py), so no CUDA library is loaded."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    b = gradient_builder(args.stops)
+    ref = oracle_gradient(args.stops)
     n_total = 1 << args.log2_samples
     count = min(n_total, 1 << 24)
     first = (n_total - count) // 2
-    from oracle import oracle
-    ref = oracle.OracleCurve(b.to_desc())
-    for _ in range(args.warmup):
-        ref.take(n_total, first, count, threads=cores)
+    out = np.zeros((count, 4), dtype=np.float32)
+    for _ in range(max(args.warmup, 1)):
+        ref.take(n_total, first, count, threads=cores, out=out)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ref.take(n_total, first, count, threads=cores)
+        ref.take(n_total, first, count, threads=cores, out=out)
     dt = time.perf_counter() - t0
     value = count * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": C5(args.log2_samples, args.stops).name,
-                   "reference": "C++ restatement of enterpolation 0.3.0 eval (oracle/; Rust toolchain unavailable)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": headline_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "threads": cores, "kind": "port",
+                         "what": "C++ restatement of enterpolation 0.3.0 eval (oracle/; Rust toolchain unavailable), "
+                                 "std::thread over contiguous index ranges, rank 0 only",
                          "sample": f"{count} consecutive samples from the middle of the 2^{args.log2_samples} take, per step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -453,7 +526,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
 
-    from enterpolation_b200 import _abi, shard_range
+    from enterpolation_b200 import _abi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -504,17 +577,44 @@ def run_gpu(args):
     ms_max = reduce_max(ms)
     total_launches = int(reduce_sum(launches))
     value = w.samples_total * args.steps / (ms_max * 1e-3)
-
-    # ---- e2e: the user-facing call with HOST buffers (build + take(n).collect() of a window) -------
     n_total = w.n_total
-    e2e_total = min(n_total, 1 << args.log2_e2e)
-    e_lo, e_hi = shard_range(e2e_total, rank, world)
-    e_first = (n_total - e2e_total) // 2 + e_lo
-    e_count = e_hi - e_lo
+    per_launch_ms = ms / args.steps  # rank 0's step (one launch; rank 0 also launches the 2^24-sample head kernel)
+    achieved = w.samples * w.bytes_per_sample / (per_launch_ms * 1e-3) / 1e9
+    c5_samples = w.samples
+    rows_kernel = w.kernel
+    builder = w.builder
+
+    # ---- the same take with 256 stops (SURVEY.md 8d "second run 256 stops": the general, non-power-of-two case) ----
+    c5_256 = None
+    if args.stops != 256:
+        try:
+            x = C5(args.log2_samples, 256, rank=rank, world=world, device=local)
+            x.builder, x.curve = gradient_builder(256), None
+            x.n_total, x.samples_total, x.lo, x.samples = w.n_total, w.samples_total, w.lo, w.samples
+            x.curve = x.builder.on_device(local).build()
+            x.curve.upload(local)
+            x.out = w.out  # same output buffer (the 64 GiB take does not fit twice)
+            xsteps = max(3, min(args.steps, 10))
+            xms_own = time_steps(x, xsteps, 3, stream, barrier)
+            xms = reduce_max(xms_own)
+            own_gbs = x.samples * 16 / (xms_own / xsteps * 1e-3) / 1e9
+            c5_256 = {"workload": c5_name(args.log2_samples, 256), "value": x.samples_total * xsteps / (xms * 1e-3),
+                      "unit": UNIT, "ms_per_step": xms / xsteps, "dtype": "f32", "kernel": x.kernel,
+                      "hbm": {"algorithmic_bytes_per_sample": 16, "achieved_gbs": own_gbs, "peak_gbs": hbm_peak,
+                              "frac": own_gbs / hbm_peak}}
+            del x
+        except Exception as ex:
+            c5_256 = {"error": repr(ex)}
+
+    # ---- e2e: the user-facing call with HOST buffers (build + take(n).collect() of a window), per-rank window ----
+    e_count = min(w.samples, 1 << args.log2_e2e)           # samples per RANK (weak in the window, like the D2H link)
+    e2e_total = e_count * world
+    e_first = w.lo + (w.samples - e_count) // 2            # the middle of this rank's shard of the take
+    del w
+    torch.cuda.empty_cache()
     host = torch.empty((e_count, 4), dtype=torch.float32, pin_memory=True)
     host.zero_()  # touch the pinned pages before timing
     table_bytes = args.stops * 16 + (args.stops + 2) * 4
-    builder = w.builder
 
     def e2e_step():
         c = builder.on_device(local).build()  # builder validation + table upload inside the timed region
@@ -532,30 +632,50 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_dt = reduce_max(time.perf_counter() - t0)
     e2e_value = e2e_total * e2e_steps / e2e_dt
-    del host
 
-    per_launch_ms = ms / args.steps  # rank 0's kernel: one launch per step
-    achieved = w.samples * w.bytes_per_sample / (per_launch_ms * 1e-3) / 1e9
-    cpu_1t = cpu_all = None
+    # The limiter, measured in the same run: plain pinned cudaMemcpyAsync D2H of the same bytes, all ranks at once.
+    probe_src = torch.empty((e_count, 4), dtype=torch.float32, device=dev)
+    probe_src.zero_()
+    for _ in range(2):
+        host.copy_(probe_src, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host.copy_(probe_src, non_blocking=True)
+        torch.cuda.synchronize()
+    probe_dt = reduce_max(time.perf_counter() - t0)
+    d2h_limit_gbs = e2e_total * 16 * e2e_steps / probe_dt / 1e9
+    del host, probe_src
+
+    cpu_1t = cpu_all = anchor = None
     if rank == 0 and world == 1:  # the CPU baseline is an N = 1 leg (at N > 1 the ranks are bound to GPU-local cores)
-        cpu_1t = w.cpu_rate(1, 1 << 22)
-        cpu_all = w.cpu_rate(cores, 1 << 25)
-    c5_samples = w.samples
-    c5_name = w.name
-    rows_kernel = w.kernel
-    del w
+        ref = oracle_gradient(args.stops)
+        n1, na = 1 << 22, 1 << 24
+        out1 = np.zeros((na, 4), dtype=np.float32)
+        cpu_1t = best_rate(lambda: ref.take(n_total, (n_total - n1) // 2, n1, threads=1, out=out1[:n1]), n1)
+        cpu_all = best_rate(lambda: ref.take(n_total, (n_total - na) // 2, na, threads=cores, out=out1), na)
+        del out1
+        try:
+            anchor = readme_anchor()
+        except Exception as ex:
+            anchor = {"error": repr(ex)}
     torch.cuda.empty_cache()
 
     # ---- the other BASELINE.json configs, briefly ---------------------------------------------------
     extra = {}
+    if c5_256 is not None:
+        extra["C5_256"] = c5_256
     if not args.no_extra:
         for cls in (C1, C2, C3, C4):
             try:
                 x = cls(rank=rank, world=world, device=local).setup()
                 xsteps = 10
-                xms = reduce_max(time_steps(x, xsteps, 3, stream, barrier))
+                xms_own = time_steps(x, xsteps, 3, stream, barrier)
+                xms = reduce_max(xms_own)
                 xval = x.samples_total * xsteps / (xms * 1e-3)
-                own = x.samples / (xms / xsteps * 1e-3)  # this rank's kernel
+                own = x.samples / (xms_own / xsteps * 1e-3)  # this rank's kernel
+                theo = FP64_LANE_OPS_THEORETICAL if x.fp_peak == FP64_LANE_OPS else FP32_LANE_OPS_THEORETICAL
                 entry = {
                     "workload": x.name, "value": xval, "unit": UNIT, "ms_per_step": xms / xsteps, "dtype": x.dtype,
                     "kernel": x.kernel,
@@ -563,9 +683,12 @@ def run_gpu(args):
                             "achieved_gbs": own * x.bytes_per_sample / 1e9, "peak_gbs": hbm_peak,
                             "frac": own * x.bytes_per_sample / 1e9 / hbm_peak},
                     "fp_pipe": {"exact_order_fp_ops_per_sample": x.fp_ops_per_sample,
-                                "achieved_lane_ops_per_s": own * x.fp_ops_per_sample, "peak_lane_ops_per_s": x.fp_peak,
-                                "frac": own * x.fp_ops_per_sample / x.fp_peak,
-                                "peak_source": "tools/pipebench.cu unfused FMUL/FADD (DMUL/DADD) chains, profiles/r01_pipebench.json"},
+                                "achieved_lane_ops_per_s": own * x.fp_ops_per_sample,
+                                "peak_lane_ops_per_s": x.fp_peak, "frac": own * x.fp_ops_per_sample / x.fp_peak,
+                                "peak_source": "measured: tools/pipebench.cu unfused FMUL/FADD (DMUL/DADD) chains, "
+                                               "profiles/r01_pipebench.json (~1.82 GHz under load)",
+                                "peak_theoretical_lane_ops_per_s": theo, "frac_of_theoretical": own * x.fp_ops_per_sample / theo,
+                                "peak_theoretical_source": "148 SMs x 128 (f64: 64) lanes x 1.965 GHz"},
                 }
                 if rank == 0 and world == 1:
                     entry["cpu_baseline"] = {"single_thread": x.cpu_rate(1, 1 << 20), "all_cores": x.cpu_rate(cores, 1 << 23),
@@ -581,36 +704,39 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": c5_name, "samples_total": n_total, "samples_per_rank": c5_samples,
-                       "elements": f"[f32;4] x {args.stops}",
-                       "l2_policy": "outputs (16 B/sample, %.1f GiB per rank) are larger than L2; nothing is re-read"
-                                    % (c5_samples * 16 / 2 ** 30),
-                       "parity": "bit-exact vs CPU oracle (tests/test_gpu_parity.py::test_config_shapes_small)"},
+            "config": headline_config(args),
+            "samples_per_rank": c5_samples,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": table_bytes,
                     "d2h_bytes_per_step": e_count * 16,
-                    "what": f"builder.build() + enterp_take_host over a {e2e_total}-sample window of the "
+                    "window": "weak: %d samples per rank from the middle of each rank's shard" % e_count,
+                    "achieved_gbs": e2e_value * 16 / 1e9, "limit_gbs": d2h_limit_gbs,
+                    "frac_of_limit": e2e_value * 16 / 1e9 / d2h_limit_gbs,
+                    "limit_source": "plain pinned cudaMemcpyAsync D2H of the same bytes on every rank at once, same run",
+                    "what": f"builder.build() + enterp_take_host over a {e_count}-sample window per rank of the "
                             f"2^{args.log2_samples} take (pinned host buffer, chunked kernel/D2H pipeline), "
                             f"{e2e_steps} steps, wall clock max over ranks"},
             "gpu_launches": total_launches, "numa_bound": bool(numa_bound),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         # ncu --set full of this kernel on a 2^30-sample launch (profiles/r01_ncu_c5_rows_final.txt):
-                         # dram__bytes_write.sum 17.12 GB + dram__bytes_read.sum 0.25 MB = 15.95 B/sample, scaled
-                         # to this launch's sample count
+                         # ncu --set full of this kernel on a 2^30-sample launch: DRAM bytes per sample, scaled to this
+                         # launch's sample count
                          "traffic": c5_samples * NCU_C5_DRAM_BYTES_PER_SAMPLE / 1e9, "traffic_unit": "GB per launch",
-                         "traffic_source": "profiles/r01_ncu_c5_rows_final.txt (per-sample DRAM bytes of a 2^30-sample "
+                         "traffic_source": "profiles/r02_ncu_c5_runs.txt (per-sample DRAM bytes of a 2^30-sample "
                                            "launch x this launch's samples)",
                          "kernel": rows_kernel,
                          "algorithmic_bytes_per_sample": 16, "peak_source": f"MEASURED_PEAKS.json ({how}, burst copy)",
-                         # FMA-pipe lane-operations the kernel has to execute per sample: 72 (six unfused merges of four
-                         # components) + 12 (six factors: subtract, multiply by the exact inverse) + 6 (1 - f) + 3 (stepper,
-                         # span) = 93; the reference's own order has 125 (it regenerates knots and divides), DESIGN.md §4
-                         "fp32_pipe_frac": c5_samples * 93 / (per_launch_ms * 1e-3) / FP32_LANE_OPS,
-                         "fp32_lane_ops_per_sample": 93, "reference_order_fp_ops_per_sample": 125},
+                         # FP work: one de Boor evaluation per DISTINCT stepper value (run length 2^(floor(log2 i)-23) for
+                         # i >= 2^24: 256 in the upper half of a take(2^32)); the per-sample kernels of round 1 needed 93
+                         # FMA-pipe lane-ops per sample (5 stops), the reference's own order 125
+                         "evaluations_per_sample": (float(1 << 24) + 8 * float(1 << 23)) / float(1 << 32)
+                         if args.log2_samples == 32 else None,
+                         "reference_order_fp_ops_per_sample": 125},
             "cpu_baseline": {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
                              "single_thread": cpu_1t,
-                             "sample": f"{1 << 25} consecutive samples (all cores) / {1 << 22} (1 thread) from the middle of the take; "
-                                       "C++ restatement of enterpolation 0.3.0 (oracle/), per-eval heap workspace as DynSpace"}
+                             "sample": f"{1 << 24} consecutive samples (all cores) / {1 << 22} (1 thread) from the middle of the take; "
+                                       "pre-touched output, 1 warm-up, best of 3; "
+                                       "C++ restatement of enterpolation 0.3.0 (oracle/), per-eval heap workspace as DynSpace",
+                             "readme_anchor": anchor}
             if world == 1 else None,
             "configs": extra,
         }

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstring>
 #include <memory>
+#include <chrono>
 #include <thread>
 #include <type_traits>
 
@@ -717,6 +718,23 @@ ORA_API uint64_t ora_eval_mt(void* c, const void* tin, uint64_t n, void* out, in
     total += inv[t];
   }
   return total;
+}
+
+// README bench shape (benches/benches.rs:62-93: `b.iter::<Vec<f64>, _>(|| curve.by_ref().take(n).collect())`):
+// `reps` sequential collects of take(n_total) into a freshly allocated vector each, single thread; returns seconds.
+ORA_API double ora_bench_take(void* c, uint64_t n_total, uint64_t reps) {
+  CurveIface* cv = static_cast<CurveIface*>(c);
+  const size_t stride = (size_t)cv->res.dim * (cv->res.scalar == ENTERP_F32 ? 4 : 8);
+  volatile unsigned char sink = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint64_t r = 0; r < reps; ++r) {
+    std::vector<unsigned char> v(stride * n_total);  // the Vec collect() allocates
+    cv->take(n_total, 0, n_total, v.data());
+    sink = sink ^ v[(size_t)(r % (stride * n_total))];
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  (void)sink;
+  return std::chrono::duration<double>(t1 - t0).count();
 }
 
 // Stepper values (signal.rs:607-609)

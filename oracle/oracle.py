@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-from enterpolation_b200 import _abi
+from . import desc as _abi  # the checker's own view of the descriptor structs: the product package is not imported
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libenterp_oracle.so")
@@ -37,7 +37,7 @@ def lib() -> C.CDLL:
         build()
     L = C.CDLL(_SO)
     vp, u64 = C.c_void_p, C.c_uint64
-    L.ora_create.argtypes = [C.POINTER(_abi.CurveDesc), C.POINTER(vp), C.POINTER(_abi.ErrorInfo)]
+    L.ora_create.argtypes = [vp, C.POINTER(vp), C.POINTER(_abi.ErrorInfo)]  # any ctypes view of enterp_curve_desc
     L.ora_create.restype = C.c_int
     L.ora_destroy.argtypes = [vp]
     L.ora_destroy.restype = None
@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
     L.ora_domain.argtypes = [vp, C.POINTER(C.c_double * 2)]
     L.ora_domain.restype = None
     L.ora_info.argtypes = [vp, C.POINTER(_abi.CurveInfo)]
+    L.ora_bench_take.argtypes = [vp, u64, u64]
+    L.ora_bench_take.restype = C.c_double
     L.ora_info.restype = None
     L.ora_eval.argtypes = [vp, vp, u64, vp]
     L.ora_eval.restype = u64
@@ -87,7 +89,7 @@ class OracleError(Exception):
 class OracleCurve:
     """A curve built by the oracle from the same descriptor the product consumes."""
 
-    def __init__(self, da: _abi.DescArrays, _handle=None, _base=None):
+    def __init__(self, da, _handle=None, _base=None):
         self._da = da
         self._base = _base  # adaptors keep the wrapped curve alive
         if _handle is not None:
@@ -97,7 +99,7 @@ class OracleCurve:
             return
         h = C.c_void_p()
         info = _abi.ErrorInfo()
-        st = lib().ora_create(C.byref(da.desc), C.byref(h), C.byref(info))
+        st = lib().ora_create(C.addressof(da.desc), C.byref(h), C.byref(info))
         if st != 0:
             info.status = st
             raise OracleError(info)
@@ -137,17 +139,21 @@ class OracleCurve:
     def _shape(self, out):
         return out.reshape(-1) if self.dim == 1 else out
 
-    def eval(self, t, threads: int = 1, return_invalid: bool = False):
+    def eval(self, t, threads: int = 1, return_invalid: bool = False, out=None):
         t = np.ascontiguousarray(np.asarray(t, dtype=self.dtype)).reshape(-1)
-        out = self._out(t.shape[0])
+        out = self._out(t.shape[0]) if out is None else out
         inv = lib().ora_eval_mt(self._h, t.ctypes.data, t.shape[0], out.ctypes.data, threads)
         return (self._shape(out), inv) if return_invalid else self._shape(out)
 
-    def take(self, n_total, first=0, count=None, threads: int = 1, return_invalid: bool = False):
+    def take(self, n_total, first=0, count=None, threads: int = 1, return_invalid: bool = False, out=None):
         count = n_total - first if count is None else count
-        out = self._out(count)
+        out = self._out(count) if out is None else out
         inv = lib().ora_take_mt(self._h, n_total, first, count, out.ctypes.data, threads)
         return (self._shape(out), inv) if return_invalid else self._shape(out)
+
+    def bench_take(self, n_total, reps) -> float:
+        """Seconds for `reps` single-threaded `take(n_total).collect()` into fresh vectors (benches/benches.rs:62-69)."""
+        return float(lib().ora_bench_take(self._h, n_total, reps))
 
     def gen_with_tangent(self, t):
         """Bezier::gen_with_tangent (bezier/mod.rs:270-276) for each t -> [n][2][dim]"""

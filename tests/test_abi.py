@@ -53,3 +53,26 @@ def test_status_strings():
     assert lib.enterp_status_str(_abi.OK) == b"ok"
     assert lib.enterp_status_str(_abi.NOT_SORTED) == b"NotSorted"
     assert b"sm_100a" in lib.enterp_version()
+
+
+def test_oracle_descriptor_view_matches_the_products():
+    """oracle/desc.py restates the descriptor structs so that the checker never imports the product package."""
+    from oracle import desc
+    for name in ("CurveDesc", "ErrorInfo", "CurveInfo"):
+        a, b = getattr(desc, name), getattr(_abi, name)
+        assert C.sizeof(a) == C.sizeof(b), name
+        assert [(f[0], f[1]) for f in a._fields_] == [(f[0], f[1]) for f in b._fields_], name
+    for const in ("LINEAR", "BEZIER", "BSPLINE", "F32", "F64", "OPEN", "CLAMPED", "LEGACY", "KNOTS_SORTED", "KNOTS_EQUIDISTANT",
+                  "EQ_BY_DEGREE", "EQ_BY_QUANTITY", "EQ_DOMAIN", "EQ_NORMALIZED", "EQ_DISTANCE", "SPACE_CONSTANT", "SPACE_DYNAMIC"):
+        assert getattr(desc, const) == getattr(_abi, const), const
+
+
+def test_reference_arm_does_not_load_the_product():
+    import subprocess
+    import sys
+    code = ("import sys; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','1','--log2-samples','20'];"
+            "import bench; bench.main(); assert 'enterpolation_b200' not in sys.modules; "
+            "assert not any('libenterp_b200' in l for l in open('/proc/self/maps'))")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert '"impl": "reference"' in r.stdout
