@@ -38,8 +38,8 @@ FP64_LANE_OPS = 1.80e13
 FP32_LANE_OPS_THEORETICAL = 148 * 128 * 1.965e9
 FP64_LANE_OPS_THEORETICAL = 148 * 64 * 1.965e9
 # ncu --set full of the stepper-run kernel bspline_rows_kernel<float,4,0,3,1,1,4> on a 2^30-sample launch
-# (profiles/r02_ncu_c5_runs.txt): (dram__bytes_write.sum + dram__bytes_read.sum) / samples
-NCU_C5_DRAM_BYTES_PER_SAMPLE = 16.0
+# (profiles/r02_ncu_c5_runs.txt): (dram__bytes_write.sum + dram__bytes_read.sum) of both launches of a step / samples
+NCU_C5_DRAM_BYTES_PER_SAMPLE = (16.851780e9 + 92.9e3 + 0.208069e9 + 11.0e3) / (1 << 30)  # runs kernel + 2^24-sample head
 
 # ---- deterministic synthetic inputs: splitmix64(seed + index) ----------------------
 def splitmix64(idx, seed):
