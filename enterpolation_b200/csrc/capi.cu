@@ -375,7 +375,7 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   d.n_top = rp.n_top;
   d.top_bytes = rp.top_bytes;
   d.bkt = static_cast<const uint32_t*>(rp.buckets);
-  d.n_bkt = rp.buckets ? (uint32_t)r.buckets.size() : 0;
+  d.n_bkt = rp.buckets ? r.n_buckets : 0;
   d.bkt_first = (R)r.bkt_first;
   d.bkt_inv = (R)r.bkt_inv;
   d.n_elem = (uint32_t)r.n_elem;

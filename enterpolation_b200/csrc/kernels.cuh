@@ -34,7 +34,7 @@ struct CurveDev {
   int n_lvl;
   int n_top;           // levels [0, n_top) are staged into shared memory by the kernel (0: none)
   uint32_t top_bytes;  // their total size (multiple of 32)
-  // Bucket index of the searched knot range (resolve.hpp), or nullptr: n_bkt words, prefix count | count << 29
+  // Bucket index of the searched knot range (resolve.hpp), or nullptr: n_bkt buckets, one 16-byte word per 32 of them
   const uint32_t* bkt;
   uint32_t n_bkt;
   R bkt_first, bkt_inv;
@@ -295,7 +295,7 @@ struct Node<double> {
 // `top`: shared-memory copy of levels [0, n_top) (nullptr when nothing is staged).
 __device__ __forceinline__ uint32_t bucket_sat_u32(float v) { return __float2uint_rz(v); }   // saturating above 2^32
 __device__ __forceinline__ uint32_t bucket_sat_u32(double v) { return __double2uint_rz(v); }
-constexpr uint32_t BUCKET_SCAN = 4;  // knots compared inside one bucket before falling back to the tree (resolve.cpp)
+constexpr uint32_t BUCKET_SCAN = 3;  // knots compared inside one bucket (2-bit counts are exact up to 3; resolve.cpp)
 
 // Pivot-tree descent (below). `top`: shared-memory copy of levels [0, n_top) (nullptr when nothing is staged).
 template <class R>
@@ -305,20 +305,32 @@ __device__ __forceinline__ uint32_t count_le_tree(const CurveDev<R>& c, R x, con
 // every knot of a lower bucket is < x and every knot of a higher bucket is > x; only the knots sharing x's bucket
 // (usually none or one) are compared. NaN lands in bucket 0 and compares false everywhere (count 0, as the
 // reference's search returns its lower bound for NaN).
+// One 16-byte word per block of 32 buckets: { knots in lower blocks, 2-bit counts of buckets 0..15, of 16..31, crowded }.
+// Returns false when there is no index or x falls into a crowded block (the caller descends the tree); otherwise
+// lo = knots in lower buckets, cnt = knots in x's bucket (0..3).
+template <class R>
+__device__ __forceinline__ bool bucket_lookup(const CurveDev<R>& c, R x, uint32_t& lo, uint32_t& cnt) {
+  if (c.bkt == nullptr) return false;
+  const R tq = xmul(xsub(x, c.bkt_first), c.bkt_inv);
+  // NaN must land in bucket 0 explicitly: the f64 -> u32 conversion does not map NaN to 0 (measured on sm_100a)
+  const uint32_t b = min(tq >= R(0) ? bucket_sat_u32(tq) : 0u, c.n_bkt - 1u);
+  const uint4 w = __ldg(reinterpret_cast<const uint4*>(c.bkt) + (b >> 5));
+  const uint32_t p = b & 31u;
+  // fields below p: all of w.y when p >= 16, and the low 2*(p & 15) bits of the word that holds p
+  const uint32_t own = p < 16u ? w.y : w.z;
+  const uint32_t part = own & ((1u << (2u * (p & 15u))) - 1u);
+  const uint32_t full = p < 16u ? 0u : w.y;
+  lo = w.x + __popc(part & 0x55555555u) + 2u * __popc(part & 0xAAAAAAAAu) + __popc(full & 0x55555555u) +
+       2u * __popc(full & 0xAAAAAAAAu);
+  cnt = (own >> (2u * (p & 15u))) & 3u;
+  return w.w == 0u;
+}
+
 template <class R>
 __device__ __forceinline__ uint32_t count_le(const CurveDev<R>& c, R x, const R* __restrict__ top = nullptr) {
-  uint32_t lo = 0, hi = 0;
-  bool tree = c.bkt == nullptr;
-  if (!tree) {
-    const R tq = xmul(xsub(x, c.bkt_first), c.bkt_inv);
-    // NaN must land in bucket 0 explicitly: the f64 -> u32 conversion does not map NaN to 0 (measured on sm_100a)
-    const uint32_t b = min(tq >= R(0) ? bucket_sat_u32(tq) : 0u, c.n_bkt - 1u);
-    const uint32_t e = __ldg(c.bkt + b);  // prefix count (29 bits) | knots in the bucket, saturated at 7 (3 bits)
-    lo = e & 0x1FFFFFFFu;
-    hi = lo + (e >> 29);
-    tree = hi - lo > BUCKET_SCAN;
-  }
-  if (tree) return count_le_tree(c, x, top);  // one call site: the unrolled descent is big
+  uint32_t lo, hi;
+  if (!bucket_lookup(c, x, lo, hi)) return count_le_tree(c, x, top);  // one call site: the unrolled descent is big
+  hi += lo;
   const R* __restrict__ k = c.ik + c.imin + lo;
   uint32_t cnt = lo;
 #pragma unroll
@@ -458,9 +470,33 @@ __device__ __forceinline__ void store_elem(R* __restrict__ out, unsigned long lo
   }
 }
 
+// 12- and 24-byte elements ([R;3]): a per-thread store instruction of a warp strides its lanes over 3 (6) lines and
+// half-fills every sector it touches, three times over (C2, ncu: 1.9 GB through the L1->XBAR port for 0.8 GB of
+// output, on the port that also carries the gathers and sat at 88 % busy). Full warps therefore park their 32
+// elements in shared memory and write them back as whole 16-byte words: 384 (768) contiguous bytes, every line once.
+template <class R, int D>
+__host__ __device__ constexpr bool stage_stores() { return D == 3; }  // 12 B ([f32;3]) and 24 B ([f64;3]); everything else stores whole sectors per lane pair
+template <class R, int D>
+__device__ __forceinline__ void store_warp_staged(R* __restrict__ out_warp, const R (&v)[D], R* __restrict__ stage_warp) {
+  const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int k = 0; k < D; ++k) stage_warp[lane * D + k] = v[k];
+  __syncwarp();
+  constexpr int N16 = 32 * D * (int)sizeof(R) / 16;
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(stage_warp);
+  float4* __restrict__ dst = reinterpret_cast<float4*>(out_warp);
+#pragma unroll
+  for (int q = 0; q < (N16 + 31) / 32; ++q)
+    if (q * 32 + (int)lane < N16) __stcs(dst + q * 32 + lane, src[q * 32 + lane]);
+  __syncwarp();
+}
+
+// `stage`: shared-memory scratch of blockDim.x * D values (only touched when stage_stores<R, D>()), `full_warp`:
+// warp-uniform, all 32 lanes hold consecutive samples i .. i + 31 of the launch (lane 0's i a multiple of 32).
 template <class R, int DH, bool PROJ>
 __device__ __forceinline__ void finish_and_store(R* __restrict__ out, unsigned long long i, const R* w0, bool valid,
-                                                 bool vec_ok, unsigned long long* invalid) {
+                                                 bool vec_ok, unsigned long long* invalid, R* __restrict__ stage = nullptr,
+                                                 bool full_warp = false) {
   constexpr int D = PROJ ? DH - 1 : DH;
   R v[D];
   if (PROJ) {
@@ -476,6 +512,13 @@ __device__ __forceinline__ void finish_and_store(R* __restrict__ out, unsigned l
 #pragma unroll
     for (int k = 0; k < D; ++k) v[k] = qnan(R(0));
     atomicAdd(invalid, 1ull);
+  }
+  if constexpr (stage_stores<R, D>()) {
+    if (full_warp && vec_ok) {  // vec_ok: out is 16-byte aligned, and so is every 32-sample group of it
+      const unsigned long long i0 = i - (threadIdx.x & 31u);
+      store_warp_staged<R, D>(out + i0 * D, v, stage + (threadIdx.x & ~31u) * D);
+      return;
+    }
   }
   store_elem<R, D>(out, i, v, vec_ok);
 }
@@ -534,10 +577,13 @@ __global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   const R* __restrict__ top = EQUI ? nullptr : stage_top_levels(c, smem_raw, &mbar);
+  constexpr int D_OUT = PROJ ? DH - 1 : DH;
+  __shared__ __align__(16) R stage[stage_stores<R, D_OUT>() ? bspline_block_cap<R>(DEG, DH) * D_OUT : 1];
   for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < s.count;
        base += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long i = base + threadIdx.x;
     const bool active = i < s.count;
+    const bool full_warp = base + (threadIdx.x | 31u) < s.count;
     R x = active ? apply_pre(c, sample_param(s, i)) : c.eq_first;
     uint32_t index;
     bool valid = bspline_span<R, EQUI>(c, x, index, top);
@@ -593,7 +639,7 @@ __global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(
         }
       }
     }
-    finish_and_store<R, DH, PROJ>(out, i, ws, valid, vec_ok, c.invalid);
+    finish_and_store<R, DH, PROJ>(out, i, ws, valid, vec_ok, c.invalid, stage, full_warp);
   }
 }
 
@@ -612,10 +658,13 @@ __global__ void __launch_bounds__(MAX_BLOCK) linear_kernel(const CurveDev<R> c, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   const R* __restrict__ top = EQUI ? nullptr : stage_top_levels(c, smem_raw, &mbar);
+  constexpr int D_OUT = PROJ ? DH - 1 : DH;
+  __shared__ __align__(16) R stage[stage_stores<R, D_OUT>() ? MAX_BLOCK * D_OUT : 1];
   for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < s.count;
        base += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long i = base + threadIdx.x;
     const bool active = i < s.count;
+    const bool full_warp = base + (threadIdx.x | 31u) < s.count;
     R x = active ? apply_pre(c, sample_param(s, i)) : R(0);
     uint32_t imin, imax;
     R f;
@@ -625,14 +674,41 @@ __global__ void __launch_bounds__(MAX_BLOCK) linear_kernel(const CurveDev<R> c, 
       // sorted knots with an interval-record table: search, then ONE vector load brings both knots and
       // both elements of the interval (list.rs:169-203 upper_border; linear/mod.rs:122-128)
       constexpr int STRIDE = linear_rec_stride<R>(DH);
+      constexpr bool A32 = (STRIDE * (int)sizeof(R)) % 32 == 0;
       const uint32_t len = c.inner_len;
-      const uint32_t m = count_le(c, x, top);
-      const bool edge = (m == len) || (m == 0);
-      imax = m == len ? len - 1 : (m == 0 ? 1u : m);
-      imin = imax - 1;
-      if (!active) continue;
+      // interval that serves a search result m (list.rs:169-203): m - 1, clamped to [0, len - 2]
+      auto interval_of = [len](uint32_t m) { return m == 0u ? 0u : (m >= len ? len - 2u : m - 1u); };
       R rec[STRIDE];
-      load_vec<STRIDE, (STRIDE * (int)sizeof(R)) % 32 == 0>(c.records + (size_t)imin * STRIDE, rec);
+      uint32_t m, cn;
+      if (bucket_lookup(c, x, m, cn)) {
+        // The interval records carry the knots themselves: record interval_of(m) holds knot m (slot 1, or slot 0 for
+        // m == 0), so the compare against the <= 3 knots of x's bucket walks the records it would fetch anyway and the
+        // knot array is never touched: one index word + one record for the ~95 % of samples whose bucket is empty.
+        const uint32_t stop = m + cn;
+        uint32_t j = interval_of(m);
+        load_vec<STRIDE, A32>(c.records + (size_t)j * STRIDE, rec);
+#pragma unroll
+        for (uint32_t q = 0; q < BUCKET_SCAN; ++q) {
+          if (m < stop && ((m == 0u ? rec[0] : rec[1]) <= x)) {
+            ++m;
+            const uint32_t jn = interval_of(m);
+            if (jn != j) {
+              j = jn;
+              load_vec<STRIDE, A32>(c.records + (size_t)j * STRIDE, rec);
+            }
+          } else {
+            break;
+          }
+        }
+        imin = j;
+      } else {
+        m = count_le_tree(c, x, top);
+        imin = interval_of(m);
+        load_vec<STRIDE, A32>(c.records + (size_t)imin * STRIDE, rec);
+      }
+      const bool edge = (m == len) || (m == 0);
+      imax = imin + 1;
+      if (!active) continue;
       const R div = xsub(rec[1], rec[0]);
       f = (edge && div == R(0)) ? div : xdiv(xsub(x, rec[0]), div);
       if (c.easing) f = apply_easing(c, f);
@@ -657,7 +733,7 @@ __global__ void __launch_bounds__(MAX_BLOCK) linear_kernel(const CurveDev<R> c, 
         for (int k = 0; k < DH; ++k) w[k] = merge1(__ldg(a + k), __ldg(b + k), f, omf);
       }
     }
-    finish_and_store<R, DH, PROJ>(out, i, w, valid, vec_ok, c.invalid);
+    finish_and_store<R, DH, PROJ>(out, i, w, valid, vec_ok, c.invalid, stage, full_warp);
   }
 }
 

@@ -398,54 +398,72 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
 
 // Bucket index of the sorted search (resolve.hpp), for 32 knots and up — small tables gain too (256 knots, random batch:
 // Linear 114 -> 160, cubic B-spline 67 -> 84 G samples/s: one L1-resident lookup instead of a three-level descent) — and only
-// when the knots spread over the buckets: the kernel compares at most
-// BUCKET_SCAN knots of a bucket and falls back to the pivot tree beyond that.
-constexpr uint32_t BUCKET_SCAN = 4;
+// when the knots spread over the buckets: the kernel compares at most BUCKET_SCAN knots of a bucket and falls back to the
+// pivot tree for blocks that hold a more crowded bucket.
+//
+// Succinct layout (round 2): one 16-byte word per block of 32 buckets = { prefix: knots in all lower blocks, 32 two-bit
+// knot counts (0..3, exact), flag: some bucket of the block holds more than 3 knots }. The knots below bucket b of its
+// block are a masked popcount away, so 16 buckets per knot cost 8 bits per knot instead of the 64 of the 4-byte-per-bucket
+// table of round 1: C2's index shrinks from 32 MB (8 buckets per knot, capped) to 8 MB (16 per knot) and shares the L2
+// with the 32 MB of interval records behind it (r01: L2 hit rate 51 %, 42 DRAM bytes per sample for 16 algorithmic).
+constexpr uint32_t BUCKET_SCAN = 3;
 template <class R>
 uint32_t bucket_of(R x, R first, R inv, uint32_t n_buckets) {
-  const R t = (x - first) * inv;  // same two IEEE operations as the kernel (count_le, kernels.cuh)
+  const R t = (x - first) * inv;  // same two IEEE operations as the kernel (bucket_lookup, kernels.cuh)
   const uint32_t b = !(t >= R(0)) ? 0u : (t >= R(4294967295.0) ? 0xFFFFFFFFu : (uint32_t)t);
   return b < n_buckets - 1u ? b : n_buckets - 1u;
 }
 template <class R>
 void build_buckets(Resolved& r, const R* knots, uint64_t n) {
   r.buckets.clear();
+  r.n_buckets = 0;
   if (n < 32 || n >= (1ull << 29)) return;
   const R first = knots[0], last = knots[n - 1];
   if (!(last > first) || !std::isfinite(first) || !std::isfinite(last)) return;
-  uint64_t nb = 1;
-  // Many buckets per knot: with 8 per knot 88 % of the buckets are empty for evenly spread knots, so most lookups
-  // touch no knot at all. Measured with 4-byte entries on one box (C2, 2^20 knots / C4, 2^16 knots; G samples/s):
-  // 2 per knot 74.4 / 30.2, 4: 82.6 / 31.1, 8: 94.7 / 31.4, 16 (C2 capped at 8): 94.8 / 31.7. The cap keeps the
-  // table at 32 MB so that it shares L2 with the tables behind it (8-byte entries at 8 per knot, 64 MB: 61 G/s).
+  uint64_t nb = 32;
+  // Many buckets per knot: with 16 per knot 94 % of the buckets are empty for evenly spread knots, so most lookups
+  // touch no knot at all (r01, 4-byte entries, C2 / C4 in G samples/s: 2 per knot 74.4 / 30.2, 4: 82.6 / 31.1,
+  // 8: 94.7 / 31.4). The cap keeps the index at 16 MB.
   uint64_t per_knot = 16;
-  if (const char* e = std::getenv("ENTERP_BUCKETS_PER_KNOT")) {  // ablation: 1, 2, 4, 8, 16
+  if (const char* e = std::getenv("ENTERP_BUCKETS_PER_KNOT")) {  // ablation: 1, 2, 4, 8, 16, ...
     const long v = std::atol(e);
     if (v >= 1 && v <= 64) per_knot = (uint64_t)v;
   }
   while (nb < per_knot * n) nb <<= 1;
-  if (nb > (1ull << 23)) nb = 1ull << 23;
+  if (nb > (1ull << 25)) nb = 1ull << 25;
   const R width = last - first;
   const R inv = (R)nb / width;
   if (!std::isfinite(width) || !std::isfinite(inv) || !(inv > R(0))) return;
-  std::vector<uint32_t> tab(nb, 0);  // prefix count (29 bits) | knots in the bucket saturated at 7 (3 bits): one 4-byte load
-  uint64_t crowded = 0;  // knots living in buckets the kernel would not scan
-  uint32_t prev = 0;
+  const uint64_t n_blocks = nb / 32;
+  std::vector<uint32_t> tab(n_blocks * 4, 0);  // per block: prefix, counts[0..16), counts[16..32), crowded flag
   std::vector<uint32_t> cnt(nb, 0);
+  uint32_t prev = 0;
   for (uint64_t i = 0; i < n; ++i) {
     const uint32_t b = bucket_of<R>(knots[i], first, inv, (uint32_t)nb);
     if (b < prev) return;  // cannot happen for sorted knots (bucket_of is monotone); be safe
     prev = b;
     ++cnt[b];
   }
+  uint64_t crowded = 0;  // knots living in blocks the kernel hands to the tree
   uint32_t run = 0;
-  for (uint64_t b = 0; b < nb; ++b) {
-    tab[b] = run | ((cnt[b] < 7u ? cnt[b] : 7u) << 29);  // > BUCKET_SCAN reads as "crowded" in the kernel
-    run += cnt[b];
-    if (cnt[b] > BUCKET_SCAN) crowded += cnt[b];
+  for (uint64_t blk = 0; blk < n_blocks; ++blk) {
+    uint32_t* w = tab.data() + blk * 4;
+    w[0] = run;
+    uint32_t in_block = 0;
+    bool over = false;
+    for (uint32_t q = 0; q < 32; ++q) {
+      const uint32_t c = cnt[blk * 32 + q];
+      in_block += c;
+      if (c > BUCKET_SCAN) over = true;
+      w[1 + (q >> 4)] |= (c < 3u ? c : 3u) << (2u * (q & 15u));
+    }
+    w[3] = over ? 1u : 0u;
+    if (over) crowded += in_block;
+    run += in_block;
   }
   if (crowded * 50 > n) return;  // more than 2 % of the knots are clustered: keep the pivot tree alone
   r.buckets = std::move(tab);
+  r.n_buckets = (uint32_t)nb;
   r.bkt_first = first;
   r.bkt_inv = inv;
 }

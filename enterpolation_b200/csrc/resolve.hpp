@@ -47,11 +47,13 @@ struct Resolved {
   // elements, lifted to homogeneous form when weighted: [n_elem][dh]
   std::vector<unsigned char> elems;
   SearchLevels levels;
-  // Bucket index over the searched knot range (sorted knots): B equal-width buckets of [first, last];
-  // buckets[b] = (number of searched knots whose bucket is < b) | min(knots in bucket b, 7) << 29. bucket(x) is the monotone
-  // function clamp(trunc((x - first) * inv), 0, B - 1) evaluated in R, so the knots <= x are those of the lower
-  // buckets plus a compare over the few knots sharing x's bucket. Empty when the knots are too clustered for it.
+  // Bucket index over the searched knot range (sorted knots): n_buckets equal-width buckets of [first, last], stored
+  // as one 16-byte word per block of 32 buckets: { knots in all lower blocks, 32 x 2-bit knot counts (two words),
+  // flag: a bucket of the block holds more than 3 knots }. bucket(x) is the monotone function
+  // clamp(trunc((x - first) * inv), 0, n_buckets - 1) evaluated in R, so the knots <= x are those of the lower buckets
+  // plus a compare over the few knots sharing x's bucket. Empty when the knots are too clustered for it.
   std::vector<uint32_t> buckets;
+  uint32_t n_buckets = 0;
   double bkt_first = 0, bkt_inv = 0;
   double domain[2] = {0, 0};
   // Bezier TransformInput (base/adaptors.rs:137-139)
