@@ -95,6 +95,12 @@ static const bool g_no_buckets = [] {
   return v && v[0] == '1';
 }();
 
+// Ablation switch (env ENTERP_NO_SLOTS=1): Linear batches over sorted knots without the grid-indexed slot table.
+static const bool g_no_slots = [] {
+  const char* v = std::getenv("ENTERP_NO_SLOTS");
+  return v && v[0] == '1';
+}();
+
 // Ablation switch (env ENTERP_NO_SMEM_PIVOTS=1): leave every pivot level in global memory / L1.
 static const bool g_no_smem_pivots = [] {
   const char* v = std::getenv("ENTERP_NO_SMEM_PIVOTS");
@@ -150,6 +156,7 @@ struct Replica {
   void* elems = nullptr;
   void* rows = nullptr;
   void* records = nullptr;
+  void* slots = nullptr;                // Linear, sorted knots: grid-indexed copies of the interval records (resolve.hpp)
   void* knot_rows = nullptr;
   void* pyramid = nullptr;              // all pivot levels, top first, one allocation
   void* buckets = nullptr;              // bucket index of the sorted search (resolve.hpp)
@@ -242,6 +249,7 @@ struct CurveCore {
       cudaFree(rp->elems);
       cudaFree(rp->rows);
       cudaFree(rp->records);
+      cudaFree(rp->slots);
       cudaFree(rp->knot_rows);
       cudaFree(rp->pyramid);
       cudaFree(rp->buckets);
@@ -292,6 +300,7 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   if (e == cudaSuccess && c->core->r.rows_mode) e = put(c->core->r.rows, &rp->rows);
   if (e == cudaSuccess && c->core->r.rec_stride && !g_no_records) e = put(c->core->r.records, &rp->records);
   if (e == cudaSuccess && c->core->r.krow_stride && !g_no_records) e = put(c->core->r.knot_rows, &rp->knot_rows);
+  if (e == cudaSuccess && c->core->r.n_slots && !g_no_records && !g_no_buckets && !g_no_slots) e = put(c->core->r.slots, &rp->slots);
   rp->n_lvl = (int)c->core->r.levels.level.size();
   if (rp->n_lvl > 0 && e == cudaSuccess) {
     std::vector<unsigned char> all;
@@ -328,6 +337,7 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
     cudaFree(rp->elems);
     cudaFree(rp->rows);
     cudaFree(rp->records);
+    cudaFree(rp->slots);
     cudaFree(rp->knot_rows);
     cudaFree(rp->pyramid);
     cudaFree(rp->buckets);
@@ -366,6 +376,10 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   d.krow_lo = (uint32_t)r.degree;
   d.records = static_cast<const R*>(rp.records);
   d.rec_stride = r.rec_stride;
+  d.slots = static_cast<const R*>(rp.slots);
+  d.n_slots = rp.slots ? r.n_slots : 0;
+  d.slot_inv = (R)r.slot_inv;
+  if (r.n_store > 0) d.k_last = reinterpret_cast<const R*>(r.store.data())[r.ik_off + r.inner_len - 1];
   d.n_lvl = rp.n_lvl;
   for (int l = 0; l < MAX_LEVELS; ++l) {
     d.lvl_off[l] = rp.lvl_off[l];

@@ -9,6 +9,8 @@ template <class R, int DH, bool PROJ>
 static cudaError_t linear_pick(bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
                                cudaStream_t st) {
   if (equi) return launch_grid_stride(linear_kernel<R, DH, PROJ, true>, s.count, BLOCK, st, c, s, out, vec_ok);
+  if (c.slots != nullptr && c.records != nullptr && c.bkt != nullptr)  // big sorted knot vectors: slot table (resolve.hpp)
+    return launch_grid_stride(linear_slots_kernel<R, DH, PROJ>, s.count, BLOCK * slot_samples<R>(), st, c, s, out, vec_ok);
   return launch_searching(linear_kernel<R, DH, PROJ, false>, s.count, c.top_bytes, st, c, s, out, vec_ok);
 }
 

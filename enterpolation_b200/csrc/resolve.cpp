@@ -682,6 +682,40 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
       r.rec_stride = stride;
       r.records.resize(rec.size() * sizeof(R));
       std::memcpy(r.records.data(), rec.data(), r.records.size());
+      // slot table (resolve.hpp): only worth it when the search is the cost, i.e. for tables far beyond L1
+      const R first = inner[0], last = inner[s.inner_len - 1];
+      // Two cells per knot: ~75 % of the samples are served by their first gather, ~22 % by the second, ~3 % walk the
+      // index (C2, G samples/s: no slots 99.9, 1 cell per knot 102.5, 2: 127.2, 4: 81.6 — a 128 MB table no longer
+      // shares the L2). The table is 2 x the records; beyond 64 MiB it is not built (the index + records path stays).
+      uint64_t per_knot = 2;
+      if (const char* e = std::getenv("ENTERP_SLOTS_PER_KNOT")) {  // ablation: 0 (off), 1, 2, 4
+        const long v = std::atol(e);
+        if (v >= 0 && v <= 16) per_knot = (uint64_t)v;
+      }
+      if (per_knot > 0 && s.inner_len >= 4096 && last > first && std::isfinite(first) && std::isfinite(last) &&
+          !r.buckets.empty()) {
+        uint64_t ns = 1;
+        while (ns < per_knot * s.inner_len) ns <<= 1;
+        const bool ablation = std::getenv("ENTERP_SLOTS_PER_KNOT") != nullptr;
+        if (!ablation && (ns + 1) * stride * sizeof(R) > (64ull << 20) + stride * sizeof(R)) ns = 0;
+        while (ns > 1 && (ns + 1) * stride * sizeof(R) > (1ull << 28)) ns >>= 1;
+        const R inv = (R)ns / (last - first);
+        if (ns > 0 && std::isfinite(inv) && inv > R(0)) {
+          std::vector<R> sl((size_t)(ns + 1) * stride);
+          uint64_t p = 0;  // knots whose cell is below b
+          const uint64_t len = s.inner_len;
+          for (uint64_t b = 0; b <= ns; ++b) {
+            while (b < ns && p < len && bucket_of<R>(inner[p], first, inv, (uint32_t)ns) < b) ++p;
+            if (b == ns) p = len;
+            const uint64_t j = p == 0 ? 0 : (p >= len ? len - 2 : p - 1);
+            std::memcpy(sl.data() + b * stride, rec.data() + j * stride, stride * sizeof(R));
+          }
+          r.n_slots = (uint32_t)ns;
+          r.slot_inv = inv;
+          r.slots.resize(sl.size() * sizeof(R));
+          std::memcpy(r.slots.data(), sl.data(), r.slots.size());
+        }
+      }
     }
   }
   if (d.kind == ENTERP_LINEAR) {

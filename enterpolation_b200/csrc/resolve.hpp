@@ -67,6 +67,15 @@ struct Resolved {
   // padded to a multiple of 16 bytes, so that the lerp's operands arrive in one or two 32-byte sectors
   std::vector<unsigned char> records;
   uint32_t rec_stride = 0;  // in units of R; 0 = no record table
+  // Linear over sorted knots, batches: "slot" table = the interval records again, but indexed by an equal-width grid
+  // over [first, last] instead of by interval: slot b holds the record of the interval that contains the START of
+  // grid cell b, i.e. interval P_b - 1 with P_b = number of knots whose cell is below b (same monotone cell function
+  // as the bucket index, own resolution), clamped to [0, len - 2]; n_slots + 1 entries. One gather then serves every
+  // sample with no knot between its cell's start and itself, a second one (slot b + 1) those beyond the cell's last
+  // knot; the rest (two or more knots in the cell and x between them) falls back to index + records.
+  std::vector<unsigned char> slots;
+  uint32_t n_slots = 0;
+  double slot_inv = 0;
   // Linear easing (easing/mod.rs:86-132, plateau.rs): kind, N of smoothstart/smoothend, Plateau min/max in R
   int32_t easing = 0, easing_n = 0;
   double ease_min = 0, ease_max = 1;
