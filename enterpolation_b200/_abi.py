@@ -228,6 +228,8 @@ def make_desc(kind, scalar, elements, weights=None, *, mode=OPEN, knots=None, eq
         d.eq_a, d.eq_b = float(dt(a)), float(dt(b))
     elif const_equidistant:
         d.knot_base = KNOTS_CONST_EQUIDISTANT
+        if const_equidistant is not True:  # BSpline over ConstEquidistant<R, N>: N is given (Linear: N = n_elements)
+            d.n_knots = int(const_equidistant)
     else:
         d.knot_base = KNOTS_SORTED if kind != BEZIER else 0
     d.space, d.workspace_n = space

@@ -310,3 +310,20 @@ class BSpline:
     @staticmethod
     def director() -> BSplineBuilder:
         return BSplineBuilder(immediate=True)
+
+    @staticmethod
+    def new_const_equidistant(elements, n_knots: int, scalar="f64", workspace: int | None = None, weights=None) -> BSplineBuilder:
+        """`BSpline::new(elements, ConstEquidistant::<R, N>::new(), space)` (bspline/mod.rs:212-235 over
+        base/list.rs:566-721): N = n_knots knots i/(N-1) on [0,1], span search by ConstEquidistant's own
+        `x * (N-1)` arithmetic, degree = N - len(elements) + 1. No builder chain reaches this type upstream; the
+        constructor's checks apply. workspace=None is `DynSpace::new(degree + 1)`, an int is `ConstSpace::<N>`.
+        Returns a chain whose `.build()` yields the curve (and whose `.to_desc()` feeds the oracle)."""
+        b = BSplineBuilder(immediate=False)
+        b._scalar = _scalar_of(scalar)
+        b._const_equidistant = int(n_knots)
+        b._space = (_abi.SPACE_DYNAMIC, 0) if workspace is None else (_abi.SPACE_CONSTANT, int(workspace))
+        if weights is not None:
+            b._elements, b._weights = np.asarray(elements), np.asarray(weights)
+        else:
+            b._elements = np.asarray(elements)
+        return b._validate(_STAGE_SPACE)

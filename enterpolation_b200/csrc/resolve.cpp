@@ -69,8 +69,9 @@ Fail check_knots(const enterp_curve_desc& d, Shape& s) {
     return ok();
   }
   if (d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT) {
-    // Linear::equidistant_unchecked (src/linear/mod.rs:193-207) is the only constructor over ConstEquidistant
-    if (d.kind != ENTERP_LINEAR) return fail(ENTERP_UNSUPPORTED);
+    // Linear::equidistant_unchecked (src/linear/mod.rs:193-207), and BSpline::new(elements, ConstEquidistant::<R, N>,
+    // space) (src/bspline/mod.rs:212-235) — the generic constructor takes any SortedChain; no builder reaches it
+    if (d.kind != ENTERP_LINEAR && d.kind != ENTERP_BSPLINE) return fail(ENTERP_UNSUPPORTED);
   } else if (d.knot_base != ENTERP_KNOTS_SORTED && d.knot_base != ENTERP_KNOTS_EQUIDISTANT) {
     return fail(ENTERP_INVALID_ARGUMENT);
   }
@@ -97,7 +98,14 @@ Fail check_knots(const enterp_curve_desc& d, Shape& s) {
   }
   // BSpline
   if (d.mode < ENTERP_OPEN || d.mode > ENTERP_LEGACY) return fail(ENTERP_INVALID_ARGUMENT);
-  if (d.knot_base == ENTERP_KNOTS_SORTED) {
+  if (d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT) {
+    // BSpline::new (src/bspline/mod.rs:212-235): N = n_knots knots i/(N-1); the constructor's own checks, in its order
+    if (d.mode != ENTERP_OPEN) return fail(ENTERP_UNSUPPORTED);
+    if (k >= (1ull << 31)) return fail(ENTERP_UNSUPPORTED);
+    if (k < e || e <= k - e + 1) return fail(ENTERP_INCONGRUOUS_ELEMENTS_KNOTS, e, k, ENTERP_OPEN);
+    s.inner_len = s.virt_len = k;
+    s.adaptor = AD_NONE;
+  } else if (d.knot_base == ENTERP_KNOTS_SORTED) {
     switch (d.mode) {
       case ENTERP_OPEN:  // src/bspline/builder.rs:377-401
         if (k < 2) return fail(ENTERP_TOO_FEW_KNOTS, k);
@@ -267,6 +275,9 @@ void build_rows(const enterp_curve_desc& d, const Shape& s, Resolved& r, const R
   r.rows_mode = 0;
   const int p = (int)s.degree;
   if (s.degree < 1 || s.degree > (uint64_t)ROWS_MAX_DEGREE) return;
+  // ConstEquidistant spans come from floor(x * fl(N - 1)) (list.rs:652-664), not from comparisons with the tabulated
+  // knots: the generic kernel carries that arithmetic; no span rows
+  if (d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT) return;
   const uint64_t lo = s.degree, hi = s.virt_len - s.degree;
   const uint64_t n_rows = hi - lo + 1;
   const int W = lanes_of<R>();
@@ -605,7 +616,8 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
     r.domain[0] = vk[0];                      // src/linear/mod.rs:139-141
     r.domain[1] = vk[s.virt_len - 1];
   }
-  if (d.knot_base == ENTERP_KNOTS_EQUIDISTANT) r.eq_first = inner[r.imin < s.inner_len ? r.imin : s.inner_len - 1];
+  if (d.knot_base == ENTERP_KNOTS_EQUIDISTANT || d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT)
+    r.eq_first = inner[r.imin < s.inner_len ? r.imin : s.inner_len - 1];  // eval(min) of strict_upper_bound_clamped
 
   // Pivot tree for the sorted search: nodes are 32-byte sectors (FAN keys), bottom level = the searched
   // knot range, each upper level = last key of every node below; all NaN padded (see kernels.cuh).

@@ -72,9 +72,11 @@ typedef enum enterp_status {
 enum { ENTERP_LINEAR = 0, ENTERP_BEZIER = 1, ENTERP_BSPLINE = 2 };           /* desc.kind      */
 enum { ENTERP_F32 = 0, ENTERP_F64 = 1 };                                       /* desc.scalar    */
 enum { ENTERP_OPEN = 0, ENTERP_CLAMPED = 1, ENTERP_LEGACY = 2 };               /* desc.mode      */
-/* desc.knot_base. CONST_EQUIDISTANT (Linear only) is `Linear::equidistant_unchecked(elements)` over
- * ConstEquidistant<R, N> (src/linear/mod.rs:193-207, src/base/list.rs:566-721): knots i/(N-1) on [0,1]
- * and a span computed as x*(N-1) — different roundings from Equidistant's (x-offset)/step. */
+/* desc.knot_base. CONST_EQUIDISTANT is ConstEquidistant<R, N> (src/base/list.rs:566-721): knots i/(N-1) on [0,1]
+ * and a span computed as x*(N-1) — different roundings from Equidistant's (x-offset)/step. Linear:
+ * `Linear::equidistant_unchecked(elements)` (src/linear/mod.rs:193-207), N = n_elements. BSpline:
+ * `BSpline::new(elements, ConstEquidistant::<R, N>::new(), space)` (src/bspline/mod.rs:212-235), N = n_knots,
+ * mode OPEN only (no builder chain reaches this type; the constructor's checks apply). */
 enum { ENTERP_KNOTS_SORTED = 0, ENTERP_KNOTS_EQUIDISTANT = 1, ENTERP_KNOTS_CONST_EQUIDISTANT = 2 };
 enum { ENTERP_EQ_BY_DEGREE = 0, ENTERP_EQ_BY_QUANTITY = 1 };                   /* desc.eq_by     */
 enum { ENTERP_EQ_DOMAIN = 0, ENTERP_EQ_NORMALIZED = 1, ENTERP_EQ_DISTANCE = 2 }; /* desc.eq_form */

@@ -176,6 +176,7 @@ template <class R>
 struct Chain {
   enterp_curve_desc d{};
   std::vector<R> elements, weights, knots;
+  uint64_t const_knots = 0;  // N of ConstEquidistant<R, N> knots given to BSpline::new
   bool immediate = false;
   bool failed = false;
   enterp_status first_status = ENTERP_OK;
@@ -186,7 +187,7 @@ struct Chain {
     d.n_elements = d.dim > 0 ? elements.size() / (size_t)d.dim : 0;
     d.elements = elements.empty() ? nullptr : elements.data();
     d.weights = d.weighted ? (weights.empty() ? nullptr : weights.data()) : nullptr;
-    d.n_knots = knots.size();
+    d.n_knots = d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT ? const_knots : knots.size();
     d.knots = knots.empty() ? nullptr : knots.data();
   }
   void validate(int stage) {
@@ -338,6 +339,14 @@ class BSplineBuilder : public BuilderBase<BSplineBuilder<R>, R> {
   BSplineBuilder& knots(std::vector<R> k) {                   // 377-401 / 447-466 / 512-534
     this->c_.d.knot_base = ENTERP_KNOTS_SORTED;
     this->c_.knots = std::move(k);
+    this->c_.validate(1);
+    return *this;
+  }
+  // BSpline::new(elements, ConstEquidistant::<R, N>::new(), space) (src/bspline/mod.rs:212-235 over
+  // src/base/list.rs:566-721): N knots i/(N-1) on [0,1]; open mode only, the constructor's own checks apply
+  BSplineBuilder& const_equidistant(uint64_t n_knots) {
+    this->c_.d.knot_base = ENTERP_KNOTS_CONST_EQUIDISTANT;
+    this->c_.const_knots = n_knots;
     this->c_.validate(1);
     return *this;
   }

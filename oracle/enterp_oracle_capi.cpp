@@ -211,6 +211,15 @@ Err resolve(const enterp_curve_desc& d, Resolved& r) {
         } else {
           return err(ENTERP_UNSUPPORTED);  // no `impl` block for Legacy + equidistant
         }
+      } else if (d.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT) {
+        // BSpline::new(elements, ConstEquidistant::<R, N>::new(), space) (bspline/mod.rs:212-235): N = n_knots; no
+        // builder path exists, the constructor's own checks apply (no TooFewKnots, no sort check, no adaptor)
+        if (d.mode != ENTERP_OPEN) return err(ENTERP_UNSUPPORTED);
+        if (k < e) return err(ENTERP_INCONGRUOUS_ELEMENTS_KNOTS, e, k, ENTERP_OPEN);
+        if (e <= k - e + 1) return err(ENTERP_INCONGRUOUS_ELEMENTS_KNOTS, e, k, ENTERP_OPEN);
+        r.knot_base = ENTERP_KNOTS_CONST_EQUIDISTANT;
+        r.inner_len = r.virt_len = k;
+        r.adaptor = AD_NONE;
       } else {
         return err(ENTERP_INVALID_ARGUMENT);
       }
@@ -554,6 +563,8 @@ CurveIface* build_typed(const enterp_curve_desc& d, const Resolved& r) {
       if (r.adaptor == AD_NONE) out = with_knots(s);
       else if (r.adaptor == AD_BUFFER) out = with_knots(BorderBuffer<Sorted<R>>(s, r.border_n));
       else out = with_knots(BorderDeletion<Sorted<R>>(s));
+    } else if (r.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT) {
+      out = with_knots(ConstEquidistant<R>(r.inner_len));
     } else {
       Equidistant<R> q = make_equidistant<R>(r);
       if (r.adaptor == AD_NONE) out = with_knots(q);

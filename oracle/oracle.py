@@ -37,7 +37,7 @@ def lib() -> C.CDLL:
         build()
     L = C.CDLL(_SO)
     vp, u64 = C.c_void_p, C.c_uint64
-    L.ora_create.argtypes = [vp, C.POINTER(vp), C.POINTER(_abi.ErrorInfo)]  # any ctypes view of enterp_curve_desc
+    L.ora_create.argtypes = [vp, C.POINTER(vp), vp]  # any ctypes view of enterp_curve_desc
     L.ora_create.restype = C.c_int
     L.ora_destroy.argtypes = [vp]
     L.ora_destroy.restype = None
@@ -49,7 +49,7 @@ def lib() -> C.CDLL:
     L.ora_slice.restype = vp
     L.ora_domain.argtypes = [vp, C.POINTER(C.c_double * 2)]
     L.ora_domain.restype = None
-    L.ora_info.argtypes = [vp, C.POINTER(_abi.CurveInfo)]
+    L.ora_info.argtypes = [vp, vp]
     L.ora_bench_take.argtypes = [vp, u64, u64]
     L.ora_bench_take.restype = C.c_double
     L.ora_info.restype = None

@@ -191,3 +191,37 @@ def test_product_and_oracle_validation_agree_exhaustively(kind):
                    (info_o.found, info_o.necessary, info_o.index, info_o.mode), (kind, e, k, mode, base, by, cnt, space, ws)
         checked += 1
     assert checked > 50
+
+
+def test_bspline_over_const_equidistant_knots_validation():
+    """BSpline::new(elements, ConstEquidistant::<R, N>::new(), space) (bspline/mod.rs:212-235): the constructor's
+    checks in its order — TooFewElements, IncongruousElementsKnots::open (twice), TooSmallWorkspace — and agreement
+    of the product's validation with the oracle's over a grid."""
+    with pytest.raises(TooFewElements):
+        BSpline.new_const_equidistant([1.0], 5).build()
+    with pytest.raises(IncongruousElementsKnots) as e:
+        BSpline.new_const_equidistant([1.0, 2.0, 3.0], 2).build()          # knots.len() < elements.len()
+    assert (e.value.found, e.value.necessary, e.value.mode) == (3, 2, _abi.OPEN)
+    with pytest.raises(IncongruousElementsKnots):
+        BSpline.new_const_equidistant([1.0, 2.0, 3.0], 5).build()          # elements.len() <= degree
+    with pytest.raises(TooSmallWorkspace) as e:
+        BSpline.new_const_equidistant([1.0, 2.0, 3.0, 4.0], 5, workspace=2).build()
+    assert (e.value.found, e.value.necessary) == (2, 2)
+    c = BSpline.new_const_equidistant([1.0, 2.0, 3.0, 4.0], 5, workspace=3).build()
+    assert (c.degree, c.info.n_knots, c.info.adaptor) == (2, 5, 0)
+    assert c.domain() == [0.25, 0.75]  # knots[p-1], knots[len-p] of i/(N-1) (bspline/mod.rs:180-185)
+    lib, ol = _abi.load_library(), oracle.lib()
+    for e_n, n, mode, space, ws in itertools.product(range(0, 7), range(0, 12), (_abi.OPEN, _abi.CLAMPED, _abi.LEGACY),
+                                                     (_abi.SPACE_CONSTANT, _abi.SPACE_DYNAMIC), (0, 2, 3, 5)):
+        da = _abi.make_desc(_abi.BSPLINE, _abi.F32, np.arange(e_n, dtype=np.float32), mode=mode, const_equidistant=max(n, 0) or True,
+                            space=(space, ws))
+        da.desc.n_knots = n
+        info_p, info_o = _abi.ErrorInfo(), _abi.ErrorInfo()
+        sp = lib.enterp_curve_validate(C.byref(da.desc), 2, C.byref(info_p))
+        h = C.c_void_p()
+        so = ol.ora_create(C.byref(da.desc), C.byref(h), C.byref(info_o))
+        if h:
+            ol.ora_destroy(h)
+        assert sp == so, (e_n, n, mode, space, ws, sp, so)
+        if sp:
+            assert (info_p.found, info_p.necessary, info_p.mode) == (info_o.found, info_o.necessary, info_o.mode)

@@ -877,3 +877,21 @@ def test_first_use_inside_a_capture_is_reported():
     g2.replay()
     torch.cuda.synchronize()
     assert_bits_equal(out.cpu().numpy(), oracle.OracleCurve(b.to_desc()).take(n), "captured after upload")
+
+
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("n_el,n_kn,dim,weighted,workspace", [(6, 8, 1, 0, None), (9, 9, 3, 0, 2), (12, 15, 4, 1, 8), (40, 47, 2, 1, None),
+                                                               (5000, 5002, 3, 0, 4)])
+def test_bspline_over_const_equidistant_knots(scalar, n_el, n_kn, dim, weighted, workspace):
+    """BSpline::new(elements, ConstEquidistant::<R, N>, space) (bspline/mod.rs:212-235; span search by x * fl(N-1),
+    base/list.rs:652-664): batch, spans, take, host paths against the oracle, incl. every knot and its float neighbours,
+    NaN/inf (the reference panics: NaN output + counter)."""
+    dtype = DT[scalar]
+    rng = np.random.default_rng(n_el + dim)
+    el = rand_elements(n_el, dim, dtype, 0xCE)
+    w = (u01(n_el, 0xCF, dtype) + dtype(0.5)).astype(dtype) if weighted else None
+    b = BSpline.new_const_equidistant(el, n_kn, scalar, workspace=workspace, weights=w)
+    kn = (np.arange(n_kn, dtype=dtype) / dtype(n_kn - 1)).astype(dtype)
+    t = adversarial(kn, dtype, rng, n_random=3000)
+    t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf, -0.0, 1.0, 2.0], dtype=dtype)])
+    check_curve(b, t, what=f"bspline over ConstEquidistant<{scalar},{n_kn}>")

@@ -207,3 +207,26 @@ def test_bezier_tangent_and_derivatives():  # src/bezier/mod.rs:345-390
     for els in ([5.0],):  # bigger_workspace / constant
         one = oracle.OracleCurve(Bezier.builder().elements(els).normalized("f64").constant().to_desc())
         assert_near(one.gen_with_tangent([0.5, 0.25, 0.75]).ravel(), [5.0, 0.0, 5.0, 0.0, 5.0, 0.0], 4)
+
+
+def test_bspline_over_const_equidistant_equals_tabulated_knots():
+    """BSpline::new over ConstEquidistant<R, N> (bspline/mod.rs:212-235, base/list.rs:566-721): the knots are
+    fl(i)/fl(N-1), so away from the knots themselves (where `floor(x * (N-1))` and the comparison search may round to
+    different sides) it is the same curve as the open B-spline over those knots given explicitly."""
+    from enterpolation_b200 import BSpline
+    for dtype, scalar in ((np.float64, "f64"), (np.float32, "f32")):
+        for n_el, n_kn in ((6, 8), (9, 9), (12, 15)):
+            el = (np.arange(n_el * 2, dtype=dtype).reshape(n_el, 2) % 7) * dtype(0.5) - dtype(1.0)
+            ce = oracle.OracleCurve(BSpline.new_const_equidistant(el, n_kn, scalar).to_desc())
+            kn = (np.arange(n_kn, dtype=dtype) / dtype(n_kn - 1)).astype(dtype)
+            ex = oracle.OracleCurve(BSpline.builder().elements(el).knots(kn).dynamic().to_desc())
+            assert ce.domain() == ex.domain()
+            d0, d1 = float(ce.domain()[0]), float(ce.domain()[1])
+            t = (d0 - 0.2 + (d1 - d0 + 0.4) * (np.arange(4001, dtype=np.float64) + 0.37) / 4001).astype(dtype)
+            ia, _ = ce.span(t)
+            ib, _ = ex.span(t)
+            assert np.array_equal(ia, ib)
+            assert np.array_equal(ce.eval(t).view(np.uint8), ex.eval(t).view(np.uint8))
+    # ConstEquidistant's own doctests (list.rs:617-650) on the chain hook
+    ch = oracle.Chain.const_equidistant(11)
+    assert [ch.strict_upper_bound_clamped(x, 1, 3) for x in (-1.0, 0.15, 20.0)] == [1, 2, 3]
