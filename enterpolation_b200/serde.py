@@ -1,5 +1,12 @@
 """The reference's serde layout of built curves, as the on-disk format.
 
+UNVERIFIED AGAINST UPSTREAM: the reference ships no serde test or fixture and no Rust toolchain exists in this
+image, so nothing here has been checked against real `serde_json` output. The layout below is DERIVED from the
+`#[derive(Serialize, Deserialize)]` attributes and serde's documented data model; tests/test_serde.py pins it to
+values derived by hand from those rules, not to upstream bytes. Treat it as this package's own stable format that
+is meant to coincide with the reference's. Non-finite numbers are NOT interchangeable: serde_json writes NaN/inf
+as `null` and cannot read `null` back into an f32/f64, so `dumps` refuses them unless told otherwise.
+
 With its `serde` feature the reference derives `Serialize`/`Deserialize` on the curve types themselves
 (`src/bspline/mod.rs:61-67`, `src/linear/mod.rs:65-70`, `src/bezier/mod.rs:161-166`) and on everything they
 are generic over, so a serialised curve is the *resolved* structure the builders produced, not the builder
@@ -75,7 +82,8 @@ def _space_value(kind, n):
 
 
 def to_value(builder: _Chain):
-    """The serde data-model value (JSON-compatible Python objects) of the curve `builder.build()` yields."""
+    """The serde data-model value (JSON-compatible Python objects) of the curve `builder.build()` yields (layout
+    derived from the reference's derives, unverified against upstream output; non-finite numbers become None)."""
     curve = builder.build()
     info, res = curve.info, curve.resolved()
     dt = curve.dtype
@@ -228,11 +236,26 @@ def _fmt(x, f32):
     raise TypeError(type(x))
 
 
-def dumps(builder: _Chain) -> str:
-    """`serde_json::to_string(&curve)`-shaped text of the curve this chain builds."""
-    return _fmt(to_value(builder), builder.build().dtype == np.float32)
+def _has_null_number(v) -> bool:
+    if isinstance(v, dict):
+        return any(_has_null_number(x) for k, x in v.items() if k not in ("_phantom", "_input", "knots") or isinstance(x, (dict, list)))
+    if isinstance(v, list):
+        return any(x is None or _has_null_number(x) for x in v)
+    return False
+
+
+def dumps(builder: _Chain, allow_nonfinite: bool = False) -> str:
+    """`serde_json::to_string(&curve)`-shaped text of the curve this chain builds. Layout derived from the
+    reference's serde derives, unverified against upstream output (module docstring). NaN/inf elements, knots or
+    weights would be written as `null`, which `serde_json::from_str` cannot read back as a float: InvalidArgument
+    unless `allow_nonfinite=True` (then this package's own `loads` reads them back as NaN)."""
+    value = to_value(builder)
+    if not allow_nonfinite and _has_null_number(value):
+        raise InvalidArgument("non-finite number: serde_json would write null and could not read it back")
+    return _fmt(value, builder.build().dtype == np.float32)
 
 
 def loads(kind: str, text: str, scalar: str = "f64") -> _Chain:
-    """`serde_json::from_str::<Curve<..R..>>(text)`: the builder chain whose `.build()` is that curve."""
+    """`serde_json::from_str::<Curve<..R..>>(text)`: the builder chain whose `.build()` is that curve. Layout
+    derived from the reference's serde derives, unverified against upstream output (module docstring)."""
     return from_value(kind, json.loads(text), scalar)

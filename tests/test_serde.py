@@ -107,3 +107,14 @@ def test_rejects_foreign_shapes():
         serde.loads("bspline", '{"elements":[0.0,1.0,2.0,3.0],"knots":[0.0,1.0,2.0,3.0,4.0],"space":{"_phantom":null},"degree":3}', "f64")
     with pytest.raises(InvalidArgument):
         serde.loads("curve", "{}", "f64")
+
+
+def test_non_finite_values_are_refused():
+    """serde_json writes NaN/inf as null and cannot read null back into a float: dumps refuses them by default."""
+    b = Linear.builder().elements([1.0, float("nan"), 3.0]).knots([0.0, 1.0, 2.0])
+    with pytest.raises(InvalidArgument):
+        serde.dumps(b)
+    text = serde.dumps(b, allow_nonfinite=True)
+    assert "null" in text
+    ok = Linear.equidistant_unchecked([0.0, 1.0], "f64")  # "knots": null of ConstEquidistant is not a number
+    assert '"knots":null' in serde.dumps(ok)
