@@ -11,6 +11,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "fullsize: BASELINE.json configs at their full sizes, every sample against the oracle "
+                                       "(part of -m gpu; deselect with -m 'gpu and not fullsize')")
 
 
 def _have_gpu():

@@ -82,3 +82,52 @@ def test_c5_large_take_properties(stops):
     ref = oracle.OracleCurve(w.builder.to_desc())
     for first in (0, n // 3, n - (1 << 20)):
         assert_bits_equal(out[first:first + (1 << 20)].cpu().numpy(), ref.take(n, first, 1 << 20, threads=THREADS), f"window {first}")
+
+
+# ---- every sample of the full-size configs against the multi-threaded oracle, in slices ---------------
+def _compare_in_slices(out, n, slice_n, oracle_slice, what):
+    for lo in range(0, n, slice_n):
+        hi = min(n, lo + slice_n)
+        assert_bits_equal(out[lo:hi].cpu().numpy(), oracle_slice(lo, hi), f"{what} [{lo}, {hi})")
+
+
+@pytest.mark.fullsize
+def test_c2_every_sample_of_the_full_batch():
+    w = bench.C2(28, 20).setup()  # 2^20 knots, 2^28 random parameters
+    w.step()
+    ref = oracle.OracleCurve(w.builder.to_desc())
+    _compare_in_slices(w.out, w.samples, 1 << 24, lambda lo, hi: ref.eval(w.t[lo:hi].cpu().numpy(), threads=THREADS), "C2 2^28")
+
+
+@pytest.mark.fullsize
+def test_c3_every_curve_of_the_full_set():
+    w = bench.C3(20, 16, 256).setup()  # 2^20 curves x 256 samples
+    w.step()
+    _compare_in_slices(w.out, w.curves, 1 << 16,
+                       lambda lo, hi: oracle.bezier_many_take(w.ctrl[lo:hi].cpu().numpy(), 256, threads=THREADS), "C3 2^20 curves")
+
+
+@pytest.mark.fullsize
+def test_c4_every_sample_of_the_full_batch():
+    w = bench.C4(26, 16).setup()
+    w.step()
+    ref = oracle.OracleCurve(w.builder.to_desc())
+    _compare_in_slices(w.out, w.samples, 1 << 23, lambda lo, hi: ref.eval(w.t[lo:hi].cpu().numpy(), threads=THREADS), "C4 2^26")
+
+
+@pytest.mark.fullsize
+@pytest.mark.parametrize("stops", [5, 256])
+def test_c5_every_sample_of_take_2_32(stops):
+    """All 4 294 967 296 samples of the headline take, bit for bit against the oracle (the stepper-run kernel serves
+    everything from index 2^24 on). Needs the 64 GiB output resident; skipped on smaller devices."""
+    n = 1 << 32
+    if torch.cuda.get_device_properties(0).total_memory < 80 * 2 ** 30:
+        pytest.skip("needs 64 GiB of device memory")
+    w = bench.C5(32, stops).setup()
+    w.step()
+    ref = oracle.OracleCurve(w.builder.to_desc())
+    host = np.empty((1 << 26, 4), dtype=np.float32)
+    for lo in range(0, n, 1 << 26):
+        want = ref.take(n, lo, 1 << 26, threads=THREADS, out=host)
+        got = w.out[lo:lo + (1 << 26)].cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"C5 {stops} stops, slice at {lo}"
