@@ -454,6 +454,19 @@ def readme_anchor():
     return out
 
 
+def reference_subprocess(args, threads):
+    """samples/s of `bench.py --impl reference --cpu-threads T` run as a child process (None on failure)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--log2-samples", str(args.log2_samples), "--stops", str(args.stops), "--cpu-threads", str(threads)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        return float(json.loads(r.stdout.strip().splitlines()[-1])["value"])
+    except Exception:
+        return None
+
+
 # ---- the reference arm --------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's CPU path (C++ restatement in oracle/; the Rust crate cannot be
@@ -463,16 +476,17 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    threads = args.cpu_threads or cores
     ref = oracle_gradient(args.stops)
     n_total = 1 << args.log2_samples
-    count = min(n_total, 1 << 24)
+    count = min(n_total, 1 << (24 if threads > 1 else 22))
     first = (n_total - count) // 2
     out = np.zeros((count, 4), dtype=np.float32)
     for _ in range(max(args.warmup, 1)):
-        ref.take(n_total, first, count, threads=cores, out=out)
+        ref.take(n_total, first, count, threads=threads, out=out)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ref.take(n_total, first, count, threads=cores, out=out)
+        ref.take(n_total, first, count, threads=threads, out=out)
     dt = time.perf_counter() - t0
     value = count * args.steps / dt
     line = {
@@ -480,7 +494,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": headline_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "threads": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "threads": threads, "kind": "port",
                          "what": "C++ restatement of enterpolation 0.3.0 eval (oracle/; Rust toolchain unavailable), "
                                  "std::thread over contiguous index ranges, rank 0 only",
                          "sample": f"{count} consecutive samples from the middle of the 2^{args.log2_samples} take, per step"},
@@ -650,12 +664,11 @@ def run_gpu(args):
 
     cpu_1t = cpu_all = anchor = None
     if rank == 0 and world == 1:  # the CPU baseline is an N = 1 leg (at N > 1 the ranks are bound to GPU-local cores)
-        ref = oracle_gradient(args.stops)
-        n1, na = 1 << 22, 1 << 24
-        out1 = np.zeros((na, 4), dtype=np.float32)
-        cpu_1t = best_rate(lambda: ref.take(n_total, (n_total - n1) // 2, n1, threads=1, out=out1[:n1]), n1)
-        cpu_all = best_rate(lambda: ref.take(n_total, (n_total - na) // 2, na, threads=cores, out=out1), na)
-        del out1
+        # the reference arm itself, in a fresh process (this one holds a CUDA context, torch's thread pools and a
+        # clock sampler, which cost the all-cores oracle a third of its rate when it ran in-process): same code path,
+        # same sample, so the in-line baseline and `--impl reference` agree by construction
+        cpu_1t = reference_subprocess(args, 1)
+        cpu_all = reference_subprocess(args, cores)
         try:
             anchor = readme_anchor()
         except Exception as ex:
@@ -734,7 +747,8 @@ def run_gpu(args):
             "cpu_baseline": {"value": cpu_all, "unit": UNIT, "cores": cores, "kind": "port",
                              "single_thread": cpu_1t,
                              "sample": f"{1 << 24} consecutive samples (all cores) / {1 << 22} (1 thread) from the middle of the take; "
-                                       "pre-touched output, 1 warm-up, best of 3; "
+                                       "`bench.py --impl reference [--cpu-threads 1]` in a child process: pre-touched output, "
+                                       "1 warm-up, mean of 3 steps; "
                                        "C++ restatement of enterpolation 0.3.0 (oracle/), per-eval heap workspace as DynSpace",
                              "readme_anchor": anchor}
             if world == 1 else None,
@@ -774,6 +788,7 @@ def main():
     ap.add_argument("--log2-e2e", type=int, default=28)
     ap.add_argument("--stops", type=int, default=5)
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="reference arm: host threads (0 = all cores)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
