@@ -84,7 +84,7 @@ EXPORTS = [
     "enterp_curve_validate", "enterp_curve_create", "enterp_curve_destroy", "enterp_curve_get_info", "enterp_curve_get_resolved", "enterp_curve_domain",
     "enterp_curve_clamp", "enterp_curve_slice", "enterp_curve_upload", "enterp_eval_batch", "enterp_eval_take", "enterp_span_batch",
     "enterp_span_take", "enterp_stepper", "enterp_bezier_many_take", "enterp_bezier_tangent_batch", "enterp_bezier_derivatives_batch", "enterp_sample_host",
-    "enterp_take_host", "enterp_sample_host_multi", "enterp_take_host_multi", "enterp_host_scratch_release",
+    "enterp_take_host", "enterp_sample_host_multi", "enterp_take_host_multi", "enterp_host_scratch_release", "enterp_host_transfer_bytes",
     "enterp_host_alloc", "enterp_host_free", "enterp_invalid_count", "enterp_invalid_count_stream", "enterp_invalid_reset",
     "enterp_status_str", "enterp_last_cuda_error", "enterp_device_count", "enterp_launch_count",
     "enterp_version",
@@ -152,6 +152,8 @@ def load_library() -> C.CDLL:
     lib.enterp_sample_host_multi.restype = i32
     lib.enterp_take_host_multi.argtypes = [vp, C.POINTER(C.c_int), i32, u64, u64, u64, vp]
     lib.enterp_take_host_multi.restype = i32
+    lib.enterp_host_transfer_bytes.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.enterp_host_transfer_bytes.restype = None
     lib.enterp_host_scratch_release.argtypes = [i32]
     lib.enterp_host_scratch_release.restype = i32
     lib.enterp_invalid_count_stream.argtypes = [vp, i32, vp, C.POINTER(C.c_ulonglong)]

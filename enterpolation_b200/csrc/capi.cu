@@ -2,6 +2,10 @@
 // dispatch, and the host-buffer pipelines. No CPU evaluation path exists in this file or anywhere
 // in the library: every eval entry point ends in a kernel launch or an error status.
 #include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -11,6 +15,11 @@
 #include <tuple>
 #include <string>
 #include <vector>
+
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#include <sched.h>
 
 #include "../../include/enterp.h"
 #include "launch.hpp"
@@ -145,6 +154,7 @@ struct HostBuf {
 };
 struct HostPipe {
   HostBuf dev_in[2], dev_out[2], stage_in[2], stage_out[2];
+  HostBuf rle_stage[2];  // pinned landing buffers of the run-length transfer (distinct values only)
   cudaStream_t stream[2] = {nullptr, nullptr};
   cudaEvent_t done[2] = {nullptr, nullptr};
   bool busy = false;
@@ -152,6 +162,7 @@ struct HostPipe {
 
 struct Replica {
   int device = -1;
+  void* block = nullptr;                // ONE device allocation holding every table below (and the invalid counter)
   void* store = nullptr;
   void* elems = nullptr;
   void* rows = nullptr;
@@ -221,6 +232,7 @@ static int release_idle_pipes(int device) {
         free_buf(hp->dev_out[b], false);
         free_buf(hp->stage_in[b], true);
         free_buf(hp->stage_out[b], true);
+        free_buf(hp->rle_stage[b], true);
         if (hp->stream[b]) cudaStreamDestroy(hp->stream[b]);
         if (hp->done[b]) cudaEventDestroy(hp->done[b]);
       }
@@ -230,6 +242,140 @@ static int release_idle_pipes(int device) {
     }
   }
   return freed;
+}
+
+// ---- run-length host transfer ------------------------------------------------------------------------------------
+// An f32 take beyond index 2^24 repeats every parameter in runs of 2^ls samples (rows.cuh RUNS). For host-buffer calls
+// only the DISTINCT values cross PCIe; the host replicates them into the caller's buffer (plain copies: no curve
+// arithmetic runs on the CPU). The pool below does that replication with a few threads and streaming stores, so the
+// end-to-end rate is bounded by host memory bandwidth instead of the PCIe D2H rate.
+static std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};
+
+// Ablation switch (env ENTERP_NO_RLE=1): host-buffer takes always copy every sample over PCIe.
+static const bool g_no_rle = [] {
+  const char* v = std::getenv("ENTERP_NO_RLE");
+  return v && v[0] == '1';
+}();
+
+class FillPool {
+ public:
+  static FillPool& get() {
+    static FillPool* p = new FillPool();  // lives until process exit
+    return *p;
+  }
+  // fn(lo, hi) over [0, total) in blocks of `block`; the caller works too. One run at a time.
+  void run(uint64_t total, uint64_t block, const std::function<void(uint64_t, uint64_t)>& fn) {
+    std::lock_guard<std::mutex> serial(run_mu_);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      total_ = total;
+      block_ = block;
+      next_.store(0, std::memory_order_relaxed);
+      pending_ = (int)workers_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  FillPool() {
+    int n = 0;
+    if (const char* e = std::getenv("ENTERP_HOST_THREADS")) n = std::atoi(e);
+    if (n <= 0) {
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      n = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+      if (n > 16) n = 16;
+    }
+    if (n < 1) n = 1;
+    for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
+    for (std::thread& t : workers_) t.detach();
+  }
+  void work() {
+    for (;;) {
+      const uint64_t lo = next_.fetch_add(block_, std::memory_order_relaxed);
+      if (lo >= total_) break;
+      const uint64_t hi = lo + block_ < total_ ? lo + block_ : total_;
+      (*fn_)(lo, hi);
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+      }
+      work();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(uint64_t, uint64_t)>* fn_ = nullptr;
+  std::atomic<uint64_t> next_{0};
+  uint64_t total_ = 0, block_ = 1;
+  int pending_ = 0;
+  unsigned long long gen_ = 0;
+};
+
+// Index of the distinct value sample i reads: RN-even((i - vb) / 2^ls) — what from_usize(i) rounds to, in units of
+// 2^ls above vb (the same integer arithmetic as rows.cuh RUNS; tests/test_stepper_runs.py restates it).
+static inline uint64_t run_value_index(uint64_t i, uint64_t vb, unsigned ls) {
+  const uint64_t dd = i - vb;
+  const uint64_t hm1 = ((1ull << ls) >> 1) - 1ull;
+  const uint64_t par = ((dd >> ls) + (vb >> ls)) & 1ull;
+  return (dd + hm1 + par) >> ls;
+}
+
+// out[(i - a) * BYTES ..] = vals[m(i) * BYTES ..] for i in [a, b): walks the runs (value m ends at
+// vb + m * 2^ls + 2^(ls-1), plus the tie index when the mantissa (vb >> ls) + m is even).
+template <int BYTES>
+static void expand_runs(unsigned char* out, const unsigned char* vals, uint64_t a, uint64_t b, uint64_t vb, unsigned ls) {
+  const uint64_t half = (1ull << ls) >> 1, vq = vb >> ls;
+  uint64_t i = a, m = run_value_index(a, vb, ls);
+  while (i < b) {
+    uint64_t end = vb + (m << ls) + half + (((m + vq) & 1ull) ? 0ull : 1ull);
+    if (end > b) end = b;
+    const unsigned char* v = vals + m * BYTES;
+    unsigned char* o = out + (i - a) * BYTES;
+    const uint64_t n = end - i;
+#if defined(__SSE2__)
+    if (BYTES == 16 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+      const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(v));
+      __m128i* p = reinterpret_cast<__m128i*>(o);
+      for (uint64_t k = 0; k < n; ++k) _mm_stream_si128(p + k, x);  // streaming: the buffer is written once, never read here
+    } else
+#endif
+    {
+      for (uint64_t k = 0; k < n; ++k) std::memcpy(o + k * BYTES, v, BYTES);
+    }
+    i = end;
+    ++m;
+  }
+#if defined(__SSE2__)
+  _mm_sfence();
+#endif
+}
+
+static void expand_runs_any(size_t bytes, unsigned char* out, const unsigned char* vals, uint64_t a, uint64_t b, uint64_t vb,
+                            unsigned ls) {
+  switch (bytes) {
+    case 4: expand_runs<4>(out, vals, a, b, vb, ls); break;
+    case 8: expand_runs<8>(out, vals, a, b, vb, ls); break;
+    case 12: expand_runs<12>(out, vals, a, b, vb, ls); break;
+    default: expand_runs<16>(out, vals, a, b, vb, ls); break;
+  }
 }
 
 }  // namespace enterp
@@ -245,15 +391,7 @@ struct CurveCore {
     for (Replica* rp : replicas) {
       if (!rp) continue;
       DeviceGuard g(rp->device);
-      cudaFree(rp->store);
-      cudaFree(rp->elems);
-      cudaFree(rp->rows);
-      cudaFree(rp->records);
-      cudaFree(rp->slots);
-      cudaFree(rp->knot_rows);
-      cudaFree(rp->pyramid);
-      cudaFree(rp->buckets);
-      cudaFree(rp->invalid);
+      cudaFree(rp->block);
       delete rp;
     }
   }
@@ -288,29 +426,37 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   if (!g.ok) return ENTERP_NO_DEVICE;
   Replica* rp = new Replica();
   rp->device = device;
-  auto put = [&](const std::vector<unsigned char>& host, void** dev) -> cudaError_t {
-    *dev = nullptr;
-    if (host.empty()) return cudaSuccess;
-    cudaError_t e = cudaMalloc(dev, host.size());
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(*dev, host.data(), host.size(), cudaMemcpyHostToDevice);
+  // One allocation for all tables (256-byte aligned pieces) + the invalid counter: a build() + first eval costs one
+  // cudaMalloc, and destroying the curve one cudaFree (each of those synchronises the device; the end-to-end step of
+  // bench.py builds a fresh curve every time).
+  const Resolved& r = c->core->r;
+  struct Piece {
+    const void* src;
+    size_t bytes;
+    void** dst;
+    size_t off;
   };
-  cudaError_t e = put(c->core->r.store, &rp->store);
-  if (e == cudaSuccess) e = put(c->core->r.elems, &rp->elems);
-  if (e == cudaSuccess && c->core->r.rows_mode) e = put(c->core->r.rows, &rp->rows);
-  if (e == cudaSuccess && c->core->r.rec_stride && !g_no_records) e = put(c->core->r.records, &rp->records);
-  if (e == cudaSuccess && c->core->r.krow_stride && !g_no_records) e = put(c->core->r.knot_rows, &rp->knot_rows);
-  if (e == cudaSuccess && c->core->r.n_slots && !g_no_records && !g_no_buckets && !g_no_slots) e = put(c->core->r.slots, &rp->slots);
-  rp->n_lvl = (int)c->core->r.levels.level.size();
-  if (rp->n_lvl > 0 && e == cudaSuccess) {
-    std::vector<unsigned char> all;
-    const size_t rs = rsize(c->core->r);
+  std::vector<Piece> pieces;
+  auto want = [&](const void* src, size_t bytes, void** dst) {
+    *dst = nullptr;
+    if (bytes) pieces.push_back(Piece{src, bytes, dst, 0});
+  };
+  want(r.store.data(), r.store.size(), &rp->store);
+  want(r.elems.data(), r.elems.size(), &rp->elems);
+  if (r.rows_mode) want(r.rows.data(), r.rows.size(), &rp->rows);
+  if (r.rec_stride && !g_no_records) want(r.records.data(), r.records.size(), &rp->records);
+  if (r.krow_stride && !g_no_records) want(r.knot_rows.data(), r.knot_rows.size(), &rp->knot_rows);
+  if (r.n_slots && !g_no_records && !g_no_buckets && !g_no_slots) want(r.slots.data(), r.slots.size(), &rp->slots);
+  rp->n_lvl = (int)r.levels.level.size();
+  std::vector<unsigned char> all;  // the pivot levels, top first, contiguous
+  if (rp->n_lvl > 0) {
+    const size_t rs = rsize(r);
     for (int l = 0; l < rp->n_lvl; ++l) {
       rp->lvl_off[l] = (uint32_t)(all.size() / rs);
-      rp->lvl_last[l] = (uint32_t)(c->core->r.levels.level[l].size() / 32) - 1;  // nodes are 32-byte sectors
-      all.insert(all.end(), c->core->r.levels.level[l].begin(), c->core->r.levels.level[l].end());
+      rp->lvl_last[l] = (uint32_t)(r.levels.level[l].size() / 32) - 1;  // nodes are 32-byte sectors
+      all.insert(all.end(), r.levels.level[l].begin(), r.levels.level[l].end());
     }
-    e = put(all, &rp->pyramid);
+    want(all.data(), all.size(), &rp->pyramid);
     // Stage as many top levels as fit the per-CTA budget in shared memory (two fat CTAs per SM). Small
     // trees stay in L1 on their own; only trees whose upper levels exceed ~8 KB are worth staging.
     int n_top = 0;
@@ -322,26 +468,34 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
       rp->n_top = n_top;
     }
   }
-  if (e == cudaSuccess && !c->core->r.buckets.empty() && !g_no_buckets) {
-    const std::vector<uint32_t>& b = c->core->r.buckets;
-    e = cudaMalloc(&rp->buckets, b.size() * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemcpy(rp->buckets, b.data(), b.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (!r.buckets.empty() && !g_no_buckets) {
+    want(r.buckets.data(), r.buckets.size() * sizeof(uint32_t), &rp->buckets);
     // with the bucket index the tree is only a fallback for crowded buckets: do not spend shared memory on it
     rp->top_bytes = 0;
     rp->n_top = 0;
   }
-  if (e == cudaSuccess) e = cudaMalloc((void**)&rp->invalid, sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMemset(rp->invalid, 0, sizeof(unsigned long long));
+  size_t total = 256;  // [0, 8): the invalid counter
+  for (Piece& pc : pieces) {
+    pc.off = total;
+    total += (pc.bytes + 255) / 256 * 256;
+  }
+  cudaError_t e = cudaMalloc(&rp->block, total);
+  if (e == cudaSuccess) {
+    unsigned char* base = static_cast<unsigned char*>(rp->block);
+    if (total <= (1u << 20)) {  // small curves: one staged copy instead of one per table
+      std::vector<unsigned char> stage(total, 0);
+      for (const Piece& pc : pieces) std::memcpy(stage.data() + pc.off, pc.src, pc.bytes);
+      e = cudaMemcpy(base, stage.data(), total, cudaMemcpyHostToDevice);
+    } else {
+      e = cudaMemset(base, 0, 256);
+      for (const Piece& pc : pieces)
+        if (e == cudaSuccess) e = cudaMemcpy(base + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice);
+    }
+    for (const Piece& pc : pieces) *pc.dst = base + pc.off;
+    rp->invalid = reinterpret_cast<unsigned long long*>(base);
+  }
   if (e != cudaSuccess) {
-    cudaFree(rp->store);
-    cudaFree(rp->elems);
-    cudaFree(rp->rows);
-    cudaFree(rp->records);
-    cudaFree(rp->slots);
-    cudaFree(rp->knot_rows);
-    cudaFree(rp->pyramid);
-    cudaFree(rp->buckets);
-    cudaFree(rp->invalid);
+    cudaFree(rp->block);
     delete rp;
     return cuda_fail(e, "curve upload");
   }
@@ -580,6 +734,9 @@ struct HostLane {
   struct Pending {
     bool live = false;
     uint64_t off = 0, n = 0;
+    bool rle = false;     // run-length transfer: rle_stage[b] holds the distinct values of this chunk
+    uint64_t vb = 0;      // representable index at or below the chunk's first sample
+    unsigned ls = 0;      // log2 of the run length (fl() spacing of the chunk's binade)
   } pend[2];
 };
 
@@ -591,7 +748,10 @@ struct HostJob {
   void* out_host;
   size_t rs, out_stride;
   bool pin_in, pin_out;
+  bool rle;  // f32 take of a curve without input adaptors over a finite domain: chunks beyond 2^26 ship runs only
 };
+
+constexpr unsigned RLE_MIN_SHIFT = 2;  // runs of at least 4 samples (indices from 2^26 on)
 
 cudaError_t lane_prepare(const HostJob& j, HostLane& l) {
   HostPipe& hp = *l.hp;
@@ -603,6 +763,11 @@ cudaError_t lane_prepare(const HostJob& j, HostLane& l) {
     if ((e = ensure(hp.dev_out[b], l.chunk * j.out_stride, false)) != cudaSuccess) return e;
     if (!j.take && !j.pin_in && (e = ensure(hp.stage_in[b], l.chunk * j.rs, true)) != cudaSuccess) return e;
     if (!j.pin_out && (e = ensure(hp.stage_out[b], l.chunk * j.out_stride, true)) != cudaSuccess) return e;
+    if (j.rle) {
+      const size_t max_vals = (size_t)(l.chunk >> RLE_MIN_SHIFT) + 2;
+      if ((e = ensure(hp.dev_in[b], max_vals * j.rs, false)) != cudaSuccess) return e;
+      if ((e = ensure(hp.rle_stage[b], max_vals * j.out_stride, true)) != cudaSuccess) return e;
+    }
   }
   return cudaSuccess;
 }
@@ -611,9 +776,20 @@ cudaError_t lane_retire(const HostJob& j, HostLane& l, int b) {
   if (!l.pend[b].live) return cudaSuccess;
   const cudaError_t e = cudaEventSynchronize(l.hp->done[b]);
   if (e != cudaSuccess) return e;
-  if (!j.pin_out)
+  if (l.pend[b].rle) {
+    // replicate the distinct values into the caller's buffer (pinned or pageable alike), a few threads wide
+    const HostLane::Pending pd = l.pend[b];
+    const uint64_t a = j.first + l.off0 + pd.off;
+    unsigned char* dst = static_cast<unsigned char*>(j.out_host) + (l.off0 + pd.off) * j.out_stride;
+    const unsigned char* vals = static_cast<const unsigned char*>(l.hp->rle_stage[b].p);
+    const size_t stride = j.out_stride;
+    FillPool::get().run(pd.n, 1u << 16, [&](uint64_t lo, uint64_t hi) {
+      expand_runs_any(stride, dst + lo * stride, vals, a + lo, a + hi, pd.vb, pd.ls);
+    });
+  } else if (!j.pin_out) {
     std::memcpy(static_cast<char*>(j.out_host) + (l.off0 + l.pend[b].off) * j.out_stride, l.hp->stage_out[b].p,
                 l.pend[b].n * j.out_stride);
+  }
   l.pend[b].live = false;
   return cudaSuccess;
 }
@@ -627,6 +803,34 @@ enterp_status lane_issue(const HostJob& j, HostLane& l) {
   const uint64_t off = l.next;
   const uint64_t n = l.count - off < l.chunk ? l.count - off : l.chunk;
   CK(lane_retire(j, l, b), "pipeline wait");
+  const Resolved& r = j.c->core->r;
+  if (j.rle) {
+    // all of the chunk inside one binade of the stepper index, runs of at least 2^RLE_MIN_SHIFT samples?
+    const uint64_t a = j.first + l.off0 + off, last = a + n - 1;
+    const int hb = 63 - __builtin_clzll(a | 1ull);
+    if (hb >= 24 + (int)RLE_MIN_SHIFT && hb == 63 - __builtin_clzll(last | 1ull) && n >= 4096) {
+      const unsigned ls = (unsigned)(hb - 23);
+      const uint64_t vb = (a >> ls) << ls;
+      const uint64_t nvals = ((last - vb) >> ls) + 2;
+      SampleSrc<float> ts = take_src<float>(r, j.n_total, vb >> ls, nvals);  // first/count in units of 2^ls
+      cudaError_t e = launch_stepper_strided<float>(ts, ls, static_cast<float*>(hp.dev_in[b].p), hp.stream[b]);
+      if (e != cudaSuccess) return cuda_fail(e, "stepper launch");
+      const enterp_status es = dispatch_eval<float>(*j.c, *l.rp, batch_src<float>(hp.dev_in[b].p, nvals), hp.dev_out[b].p, hp.stream[b]);
+      if (es) return es;
+      CK(cudaMemcpyAsync(hp.rle_stage[b].p, hp.dev_out[b].p, nvals * j.out_stride, cudaMemcpyDeviceToHost, hp.stream[b]), "D2H");
+      g_d2h_bytes.fetch_add(nvals * j.out_stride, std::memory_order_relaxed);
+      CK(cudaEventRecord(hp.done[b], hp.stream[b]), "cudaEventRecord");
+      l.pend[b].live = true;
+      l.pend[b].off = off;
+      l.pend[b].n = n;
+      l.pend[b].rle = true;
+      l.pend[b].vb = vb;
+      l.pend[b].ls = ls;
+      l.next = off + n;
+      ++l.k;
+      return ENTERP_OK;
+    }
+  }
   const void* t_dev = nullptr;
   if (!j.take) {
     const char* src = static_cast<const char*>(j.t_host) + (l.off0 + off) * j.rs;
@@ -635,10 +839,10 @@ enterp_status lane_issue(const HostJob& j, HostLane& l) {
       src = static_cast<const char*>(hp.stage_in[b].p);
     }
     CK(cudaMemcpyAsync(hp.dev_in[b].p, src, n * j.rs, cudaMemcpyHostToDevice, hp.stream[b]), "H2D");
+    g_h2d_bytes.fetch_add(n * j.rs, std::memory_order_relaxed);
     t_dev = hp.dev_in[b].p;
   }
   enterp_status es;
-  const Resolved& r = j.c->core->r;
   if (r.scalar == ENTERP_F32) {
     auto s = j.take ? take_src<float>(r, j.n_total, j.first + l.off0 + off, n) : batch_src<float>(t_dev, n);
     es = dispatch_eval<float>(*j.c, *l.rp, s, hp.dev_out[b].p, hp.stream[b]);
@@ -649,8 +853,10 @@ enterp_status lane_issue(const HostJob& j, HostLane& l) {
   if (es) return es;
   void* dst = j.pin_out ? static_cast<void*>(static_cast<char*>(j.out_host) + (l.off0 + off) * j.out_stride) : hp.stage_out[b].p;
   CK(cudaMemcpyAsync(dst, hp.dev_out[b].p, n * j.out_stride, cudaMemcpyDeviceToHost, hp.stream[b]), "D2H");
+  g_d2h_bytes.fetch_add(n * j.out_stride, std::memory_order_relaxed);
   CK(cudaEventRecord(hp.done[b], hp.stream[b]), "cudaEventRecord");
   l.pend[b].live = true;
+  l.pend[b].rle = false;
   l.pend[b].off = off;
   l.pend[b].n = n;
   l.next = off + n;
@@ -682,6 +888,14 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
   j.out_stride = j.rs * c->core->r.dim;
   j.pin_in = take || is_pinned(t_host);
   j.pin_out = is_pinned(out_host);
+  {
+    // run-length transfer: f32 takes that reach past 2^26, no input adaptors, finite domain (then every parameter is
+    // finite and inside the domain, no sample can make the reference panic, and the per-value batch evaluation
+    // leaves the invalid counter where the per-sample take would)
+    const Resolved& rr = c->core->r;
+    j.rle = take && !g_no_rle && rr.scalar == ENTERP_F32 && c->pre.empty() && std::isfinite(rr.domain[0]) &&
+            std::isfinite(rr.domain[1]) && n_total > (1ull << (24 + RLE_MIN_SHIFT)) && first + count > (1ull << (24 + RLE_MIN_SHIFT));
+  }
   std::vector<HostLane> lanes((size_t)n_devices);
   enterp_status st = ENTERP_OK;
   for (int g = 0; g < n_devices && st == ENTERP_OK; ++g) {
@@ -971,6 +1185,11 @@ ENTERP_API enterp_status enterp_take_host_multi(enterp_curve* c, const int* devi
 }
 
 ENTERP_API int enterp_host_scratch_release(int device) { return release_idle_pipes(device); }
+
+ENTERP_API void enterp_host_transfer_bytes(unsigned long long* h2d, unsigned long long* d2h) {
+  if (h2d) *h2d = g_h2d_bytes.load();
+  if (d2h) *d2h = g_d2h_bytes.load();
+}
 
 ENTERP_API enterp_status enterp_host_alloc(void** ptr, uint64_t bytes) {
   if (!ptr) return ENTERP_INVALID_ARGUMENT;

@@ -141,6 +141,10 @@ static cudaError_t launch_deriv_impl(int dim, const CurveDev<R>& c, const Sample
     return launch_grid_stride(stepper_kernel<R>, s.count, BLOCK, st, s, out);                                          \
   }                                                                                                                    \
   template <>                                                                                                          \
+  cudaError_t launch_stepper_strided<R>(const SampleSrc<R>& s, unsigned ls, R* out, cudaStream_t st) {                 \
+    return launch_grid_stride(stepper_strided_kernel<R>, s.count, BLOCK, st, s, ls, out);                              \
+  }                                                                                                                    \
+  template <>                                                                                                          \
   cudaError_t launch_bezier_many<R>(int dim, int n, const R* ctrl, unsigned long long n_curves, uint32_t n_ctrl,       \
                                     uint32_t samples, R step, R* out, cudaStream_t st) {                               \
     return launch_many_impl<R>(dim, n, ctrl, n_curves, n_ctrl, samples, step, out, st);                                \

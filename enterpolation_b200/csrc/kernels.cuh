@@ -1060,6 +1060,15 @@ __global__ void __launch_bounds__(BLOCK) span_kernel(const CurveDev<R> c, const 
   }
 }
 
+// Stepper values at the representable indices (s.first + j) << ls only: the distinct parameters of an f32 take beyond
+// index 2^24 (rows.cuh RUNS), for the run-length host transfer (capi.cu).
+template <class R>
+__global__ void __launch_bounds__(BLOCK) stepper_strided_kernel(const SampleSrc<R> s, unsigned ls, R* __restrict__ out) {
+  for (unsigned long long j = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; j < s.count;
+       j += (unsigned long long)gridDim.x * BLOCK)
+    out[j] = xadd(xmul(s.step, from_index((s.first + j) << ls, R(0))), s.start);
+}
+
 template <class R>
 __global__ void __launch_bounds__(BLOCK) stepper_kernel(const SampleSrc<R> s, R* __restrict__ out) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; i < s.count;

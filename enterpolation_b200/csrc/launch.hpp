@@ -94,5 +94,8 @@ cudaError_t launch_bezier_deriv(int dim, const CurveDev<R>& c, const SampleSrc<R
                                 cudaStream_t st);
 template <class R>
 cudaError_t launch_stepper(const SampleSrc<R>& s, R* out, cudaStream_t st);
+// out[j] = step * fl((s.first + j) << ls) + start for j in [0, s.count)
+template <class R>
+cudaError_t launch_stepper_strided(const SampleSrc<R>& s, unsigned ls, R* out, cudaStream_t st);
 
 }  // namespace enterp

@@ -248,6 +248,14 @@ ENTERP_API enterp_status enterp_sample_host_multi(enterp_curve* curve, const int
                                                   const void* t_host, uint64_t n, void* out_host);
 ENTERP_API enterp_status enterp_take_host_multi(enterp_curve* curve, const int* devices, int n_devices,
                                                 uint64_t n_total, uint64_t first, uint64_t count, void* out_host);
+/* Run-length transfer: an f32 take repeats every parameter in runs of 2^(floor(log2 i) - 23) samples beyond index 2^24
+ * (Equidistant::eval computes `step * R::from_usize(i) + offset`, src/base/list.rs:416-418, and from_usize keeps 24
+ * bits). For such ranges (from 2^26 on; curve without input adaptors, finite domain) the take_host calls evaluate and
+ * copy only the DISTINCT values over PCIe and replicate them into out_host on the host with a few threads
+ * (ENTERP_HOST_THREADS, default: the calling thread's CPU affinity, at most 16) — byte copies only, the result is the
+ * same array bit for bit. enterp_host_transfer_bytes reports the bytes the host-buffer calls have actually moved over
+ * PCIe so far in this process (either pointer may be NULL). */
+ENTERP_API void enterp_host_transfer_bytes(unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 /* The host-buffer calls borrow pooled scratch (2 device chunk buffers, 2 streams, optional pinned staging) that is
  * kept for the next call. This frees every idle pipe of `device` (all devices when device < 0); returns the count. */
 ENTERP_API int enterp_host_scratch_release(int device);

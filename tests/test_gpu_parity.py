@@ -895,3 +895,50 @@ def test_bspline_over_const_equidistant_knots(scalar, n_el, n_kn, dim, weighted,
     t = adversarial(kn, dtype, rng, n_random=3000)
     t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf, -0.0, 1.0, 2.0], dtype=dtype)])
     check_curve(b, t, what=f"bspline over ConstEquidistant<{scalar},{n_kn}>")
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3, 4])
+def test_take_host_run_length_transfer(dim):
+    """Host-buffer takes of f32 curves beyond index 2^26 ship only the distinct values over PCIe and replicate them on
+    the host (capi.cu, run-length transfer): same bytes as the oracle, pageable and pinned outputs, windows that cross
+    binades and chunk boundaries, several devices; and the PCIe byte counter shows the saving."""
+    import ctypes as C
+    from enterpolation_b200.curve import Take
+    lib = _abi.load_library()
+    el = rand_elements(37, dim, np.float32, 0xA0 + dim)
+    b = BSpline.builder().clamped().elements(el).equidistant("f32").degree(3).normalized().dynamic()
+    curve = b.build()
+    ref = oracle.OracleCurve(b.to_desc())
+    n32 = 1 << 32
+    devices = list(range(torch.cuda.device_count()))
+    cases = [(n32, (1 << 31) - 3_000_000, 9_000_001),         # crosses 2^31, three chunks, unaligned
+             (n32, (1 << 26) - 5000, (1 << 23) + 77),         # starts below the threshold
+             (n32, n32 - (1 << 23) - 3, (1 << 23) + 3),       # the end of the take
+             ((1 << 29) + 12345, (1 << 28) - 17, (1 << 23) + 1)]
+    for n_total, first, count in cases:
+        want = ref.take(n_total, first, count, threads=8)
+        h2d0, d2h0 = C.c_ulonglong(0), C.c_ulonglong(0)
+        lib.enterp_host_transfer_bytes(C.byref(h2d0), C.byref(d2h0))
+        got = Take(curve, n_total, first, count).collect()      # pageable numpy output
+        h2d1, d2h1 = C.c_ulonglong(0), C.c_ulonglong(0)
+        lib.enterp_host_transfer_bytes(C.byref(h2d1), C.byref(d2h1))
+        assert_bits_equal(got, want, f"rle take_host dim {dim} [{first}, +{count}) of {n_total}")
+        moved = d2h1.value - d2h0.value
+        assert moved < count * dim * 4, "runs, not samples, crossed PCIe"
+        if first + count == n32:  # every 2^22-sample chunk of this window lies inside one binade: runs of 256 only
+            assert moved < count * dim * 4 // 64
+        pinned = torch.empty((count, dim) if dim > 1 else (count,), dtype=torch.float32, pin_memory=True)
+        arr = (C.c_int * len(devices))(*devices)
+        st = lib.enterp_take_host_multi(curve._h, arr, len(devices), n_total, first, count, pinned.data_ptr())
+        assert st == 0
+        assert_bits_equal(pinned.numpy(), want, f"rle take_host_multi dim {dim} pinned")
+    # adaptors switch the run-length transfer off (a mapped parameter could leave the valid range): still exact
+    cl = curve.clamp()
+    n_total, first, count = n32, (1 << 30) + 5, 300_001
+    d0 = C.c_ulonglong(0)
+    lib.enterp_host_transfer_bytes(None, C.byref(d0))
+    got = Take(cl, n_total, first, count).collect()
+    d1 = C.c_ulonglong(0)
+    lib.enterp_host_transfer_bytes(None, C.byref(d1))
+    assert_bits_equal(got, ref.clamp().take(n_total, first, count, threads=8), "clamped curve, plain transfer")
+    assert d1.value - d0.value == count * dim * 4
