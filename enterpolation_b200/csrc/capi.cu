@@ -154,7 +154,10 @@ struct HostBuf {
 };
 struct HostPipe {
   HostBuf dev_in[2], dev_out[2], stage_in[2], stage_out[2];
-  HostBuf rle_stage[2];  // pinned landing buffers of the run-length transfer (distinct values only)
+  HostBuf rle_t[2], rle_v[2];  // run-length pipeline: stepper values and their evaluations on the device
+  HostBuf rle_stage[2];        // ... and the pinned landing buffers of the distinct values
+  cudaStream_t rstream[2] = {nullptr, nullptr};
+  cudaEvent_t rdone[2] = {nullptr, nullptr};
   cudaStream_t stream[2] = {nullptr, nullptr};
   cudaEvent_t done[2] = {nullptr, nullptr};
   bool busy = false;
@@ -233,6 +236,10 @@ static int release_idle_pipes(int device) {
         free_buf(hp->stage_in[b], true);
         free_buf(hp->stage_out[b], true);
         free_buf(hp->rle_stage[b], true);
+        free_buf(hp->rle_t[b], false);
+        free_buf(hp->rle_v[b], false);
+        if (hp->rstream[b]) cudaStreamDestroy(hp->rstream[b]);
+        if (hp->rdone[b]) cudaEventDestroy(hp->rdone[b]);
         if (hp->stream[b]) cudaStreamDestroy(hp->stream[b]);
         if (hp->done[b]) cudaEventDestroy(hp->done[b]);
       }
@@ -254,6 +261,12 @@ static std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};
 // Ablation switch (env ENTERP_NO_RLE=1): host-buffer takes always copy every sample over PCIe.
 static const bool g_no_rle = [] {
   const char* v = std::getenv("ENTERP_NO_RLE");
+  return v && v[0] == '1';
+}();
+
+// Ablation switch (env ENTERP_RLE_ONLY=1): eligible chunks all take the run-length path (no plain chunks beside them).
+static const bool g_rle_only = [] {
+  const char* v = std::getenv("ENTERP_RLE_ONLY");
   return v && v[0] == '1';
 }();
 
@@ -725,19 +738,24 @@ cudaError_t ensure(HostBuf& b, size_t need, bool host) {
 }
 
 // One device's share of a host-buffer call: samples [off0, off0 + count) of the caller's arrays (take mode: global
-// stepper indices first + off0 ...), pushed through a borrowed pipe chunk by chunk.
+// stepper indices first + off0 ...), pushed through a borrowed pipe chunk by chunk. Two double-buffered pipelines work
+// on the share's chunks: the PLAIN one (kernel over every sample, D2H of every sample: bound by the PCIe copy engine,
+// no CPU time when the caller's buffer is pinned) and, for ranges where an f32 stepper repeats its parameter, the
+// RUN-LENGTH one (kernel and D2H over the distinct values only, the host replicates them: bound by host memory
+// bandwidth). Chunks are claimed dynamically: whenever a plain slot is free the copy engine gets the next chunk,
+// otherwise the CPU path takes it, so the call runs at (PCIe rate + host fill rate) and never below the PCIe rate,
+// whatever the host's cores are doing.
 struct HostLane {
   int device = 0;
   Replica* rp = nullptr;
   HostPipe* hp = nullptr;
-  uint64_t off0 = 0, count = 0, chunk = 0, next = 0, k = 0;
+  uint64_t off0 = 0, count = 0, chunk = 0, next = 0, k = 0, kr = 0;
   struct Pending {
     bool live = false;
     uint64_t off = 0, n = 0;
-    bool rle = false;     // run-length transfer: rle_stage[b] holds the distinct values of this chunk
-    uint64_t vb = 0;      // representable index at or below the chunk's first sample
+    uint64_t vb = 0;      // run-length chunks: representable index at or below the chunk's first sample
     unsigned ls = 0;      // log2 of the run length (fl() spacing of the chunk's binade)
-  } pend[2];
+  } pend[2], rpend[2];
 };
 
 struct HostJob {
@@ -748,7 +766,8 @@ struct HostJob {
   void* out_host;
   size_t rs, out_stride;
   bool pin_in, pin_out;
-  bool rle;  // f32 take of a curve without input adaptors over a finite domain: chunks beyond 2^26 ship runs only
+  bool rle;     // f32 take of a curve without input adaptors over a finite domain: chunks beyond 2^26 may ship runs only
+  bool hybrid;  // ... and the copy engine takes plain chunks beside them
 };
 
 constexpr unsigned RLE_MIN_SHIFT = 2;  // runs of at least 4 samples (indices from 2^26 on)
@@ -765,72 +784,64 @@ cudaError_t lane_prepare(const HostJob& j, HostLane& l) {
     if (!j.pin_out && (e = ensure(hp.stage_out[b], l.chunk * j.out_stride, true)) != cudaSuccess) return e;
     if (j.rle) {
       const size_t max_vals = (size_t)(l.chunk >> RLE_MIN_SHIFT) + 2;
-      if ((e = ensure(hp.dev_in[b], max_vals * j.rs, false)) != cudaSuccess) return e;
+      if (!hp.rstream[b] && (e = cudaStreamCreateWithFlags(&hp.rstream[b], cudaStreamNonBlocking)) != cudaSuccess) return e;
+      if (!hp.rdone[b] && (e = cudaEventCreateWithFlags(&hp.rdone[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+      if ((e = ensure(hp.rle_t[b], max_vals * j.rs, false)) != cudaSuccess) return e;
+      if ((e = ensure(hp.rle_v[b], max_vals * j.out_stride, false)) != cudaSuccess) return e;
       if ((e = ensure(hp.rle_stage[b], max_vals * j.out_stride, true)) != cudaSuccess) return e;
     }
   }
   return cudaSuccess;
 }
 
-cudaError_t lane_retire(const HostJob& j, HostLane& l, int b) {
+// Completes plain slot b (when `wait`, blocks until its copy has landed). *done = the slot is free afterwards.
+cudaError_t plain_finish(const HostJob& j, HostLane& l, int b, bool wait, bool* done) {
+  *done = true;
   if (!l.pend[b].live) return cudaSuccess;
-  const cudaError_t e = cudaEventSynchronize(l.hp->done[b]);
+  cudaError_t e = wait ? cudaEventSynchronize(l.hp->done[b]) : cudaEventQuery(l.hp->done[b]);
+  if (e == cudaErrorNotReady) {
+    *done = false;
+    return cudaSuccess;
+  }
   if (e != cudaSuccess) return e;
-  if (l.pend[b].rle) {
-    // replicate the distinct values into the caller's buffer (pinned or pageable alike), a few threads wide
-    const HostLane::Pending pd = l.pend[b];
-    const uint64_t a = j.first + l.off0 + pd.off;
-    unsigned char* dst = static_cast<unsigned char*>(j.out_host) + (l.off0 + pd.off) * j.out_stride;
-    const unsigned char* vals = static_cast<const unsigned char*>(l.hp->rle_stage[b].p);
-    const size_t stride = j.out_stride;
-    FillPool::get().run(pd.n, 1u << 16, [&](uint64_t lo, uint64_t hi) {
-      expand_runs_any(stride, dst + lo * stride, vals, a + lo, a + hi, pd.vb, pd.ls);
-    });
-  } else if (!j.pin_out) {
+  if (!j.pin_out)
     std::memcpy(static_cast<char*>(j.out_host) + (l.off0 + l.pend[b].off) * j.out_stride, l.hp->stage_out[b].p,
                 l.pend[b].n * j.out_stride);
-  }
   l.pend[b].live = false;
   return cudaSuccess;
 }
 
-// Issues the lane's next chunk (H2D of its parameters, kernel, D2H) on the pipe's stream k & 1.
-enterp_status lane_issue(const HostJob& j, HostLane& l) {
-  DeviceGuard g(l.device);
-  if (!g.ok) return ENTERP_NO_DEVICE;
+// Completes run-length slot b: waits for its (small) copy and replicates the distinct values into the caller's
+// buffer (pinned or pageable alike), a few threads wide.
+cudaError_t rle_finish(const HostJob& j, HostLane& l, int b) {
+  if (!l.rpend[b].live) return cudaSuccess;
+  const cudaError_t e = cudaEventSynchronize(l.hp->rdone[b]);
+  if (e != cudaSuccess) return e;
+  const HostLane::Pending pd = l.rpend[b];
+  const uint64_t a = j.first + l.off0 + pd.off;
+  unsigned char* dst = static_cast<unsigned char*>(j.out_host) + (l.off0 + pd.off) * j.out_stride;
+  const unsigned char* vals = static_cast<const unsigned char*>(l.hp->rle_stage[b].p);
+  const size_t stride = j.out_stride;
+  FillPool::get().run(pd.n, 1u << 16, [&](uint64_t lo, uint64_t hi) {
+    expand_runs_any(stride, dst + lo * stride, vals, a + lo, a + hi, pd.vb, pd.ls);
+  });
+  l.rpend[b].live = false;
+  return cudaSuccess;
+}
+
+// All of chunk [a, a + n) inside one binade of the stepper index, runs of at least 2^RLE_MIN_SHIFT samples?
+bool rle_eligible(const HostJob& j, uint64_t a, uint64_t n, unsigned* ls) {
+  if (!j.rle || n < 4096) return false;
+  const int hb = 63 - __builtin_clzll(a | 1ull);
+  if (hb < 24 + (int)RLE_MIN_SHIFT || hb != 63 - __builtin_clzll((a + n - 1) | 1ull)) return false;
+  *ls = (unsigned)(hb - 23);
+  return true;
+}
+
+// Plain chunk [off, off + n) of the lane on slot b (free): H2D of its parameters (batches), kernel, D2H.
+enterp_status plain_issue(const HostJob& j, HostLane& l, int b, uint64_t off, uint64_t n) {
   HostPipe& hp = *l.hp;
-  const int b = (int)(l.k & 1);
-  const uint64_t off = l.next;
-  const uint64_t n = l.count - off < l.chunk ? l.count - off : l.chunk;
-  CK(lane_retire(j, l, b), "pipeline wait");
   const Resolved& r = j.c->core->r;
-  if (j.rle) {
-    // all of the chunk inside one binade of the stepper index, runs of at least 2^RLE_MIN_SHIFT samples?
-    const uint64_t a = j.first + l.off0 + off, last = a + n - 1;
-    const int hb = 63 - __builtin_clzll(a | 1ull);
-    if (hb >= 24 + (int)RLE_MIN_SHIFT && hb == 63 - __builtin_clzll(last | 1ull) && n >= 4096) {
-      const unsigned ls = (unsigned)(hb - 23);
-      const uint64_t vb = (a >> ls) << ls;
-      const uint64_t nvals = ((last - vb) >> ls) + 2;
-      SampleSrc<float> ts = take_src<float>(r, j.n_total, vb >> ls, nvals);  // first/count in units of 2^ls
-      cudaError_t e = launch_stepper_strided<float>(ts, ls, static_cast<float*>(hp.dev_in[b].p), hp.stream[b]);
-      if (e != cudaSuccess) return cuda_fail(e, "stepper launch");
-      const enterp_status es = dispatch_eval<float>(*j.c, *l.rp, batch_src<float>(hp.dev_in[b].p, nvals), hp.dev_out[b].p, hp.stream[b]);
-      if (es) return es;
-      CK(cudaMemcpyAsync(hp.rle_stage[b].p, hp.dev_out[b].p, nvals * j.out_stride, cudaMemcpyDeviceToHost, hp.stream[b]), "D2H");
-      g_d2h_bytes.fetch_add(nvals * j.out_stride, std::memory_order_relaxed);
-      CK(cudaEventRecord(hp.done[b], hp.stream[b]), "cudaEventRecord");
-      l.pend[b].live = true;
-      l.pend[b].off = off;
-      l.pend[b].n = n;
-      l.pend[b].rle = true;
-      l.pend[b].vb = vb;
-      l.pend[b].ls = ls;
-      l.next = off + n;
-      ++l.k;
-      return ENTERP_OK;
-    }
-  }
   const void* t_dev = nullptr;
   if (!j.take) {
     const char* src = static_cast<const char*>(j.t_host) + (l.off0 + off) * j.rs;
@@ -856,11 +867,70 @@ enterp_status lane_issue(const HostJob& j, HostLane& l) {
   g_d2h_bytes.fetch_add(n * j.out_stride, std::memory_order_relaxed);
   CK(cudaEventRecord(hp.done[b], hp.stream[b]), "cudaEventRecord");
   l.pend[b].live = true;
-  l.pend[b].rle = false;
   l.pend[b].off = off;
   l.pend[b].n = n;
+  return ENTERP_OK;
+}
+
+// Run-length chunk on slot b (free): the stepper values at the representable indices, their evaluation as a batch,
+// and the D2H of those values only.
+enterp_status rle_issue(const HostJob& j, HostLane& l, int b, uint64_t off, uint64_t n, unsigned ls) {
+  HostPipe& hp = *l.hp;
+  const Resolved& r = j.c->core->r;
+  const uint64_t a = j.first + l.off0 + off;
+  const uint64_t vb = (a >> ls) << ls;
+  const uint64_t nvals = ((a + n - 1 - vb) >> ls) + 2;
+  SampleSrc<float> ts = take_src<float>(r, j.n_total, vb >> ls, nvals);  // first/count in units of 2^ls
+  const cudaError_t e = launch_stepper_strided<float>(ts, ls, static_cast<float*>(hp.rle_t[b].p), hp.rstream[b]);
+  if (e != cudaSuccess) return cuda_fail(e, "stepper launch");
+  const enterp_status es = dispatch_eval<float>(*j.c, *l.rp, batch_src<float>(hp.rle_t[b].p, nvals), hp.rle_v[b].p, hp.rstream[b]);
+  if (es) return es;
+  CK(cudaMemcpyAsync(hp.rle_stage[b].p, hp.rle_v[b].p, nvals * j.out_stride, cudaMemcpyDeviceToHost, hp.rstream[b]), "D2H");
+  g_d2h_bytes.fetch_add(nvals * j.out_stride, std::memory_order_relaxed);
+  CK(cudaEventRecord(hp.rdone[b], hp.rstream[b]), "cudaEventRecord");
+  l.rpend[b].live = true;
+  l.rpend[b].off = off;
+  l.rpend[b].n = n;
+  l.rpend[b].vb = vb;
+  l.rpend[b].ls = ls;
+  return ENTERP_OK;
+}
+
+// One unit of work for the lane: claims its next chunk for the copy engine or for the CPU path (see HostLane).
+enterp_status lane_step(const HostJob& j, HostLane& l) {
+  DeviceGuard g(l.device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  const uint64_t off = l.next;
+  const uint64_t n = l.count - off < l.chunk ? l.count - off : l.chunk;
+  unsigned ls = 0;
+  const bool eligible = rle_eligible(j, j.first + l.off0 + off, n, &ls);
+  bool done = true;
+  if (!eligible) {  // the classic double-buffered pipeline: wait for the slot used two chunks ago
+    const int b = (int)(l.k & 1);
+    CK(plain_finish(j, l, b, true, &done), "pipeline wait");
+    const enterp_status es = plain_issue(j, l, b, off, n);
+    if (es) return es;
+    ++l.k;
+    l.next = off + n;
+    return ENTERP_OK;
+  }
+  if (j.hybrid) {  // a free plain slot means an idle copy engine: feed it first
+    for (int b = 0; b < 2; ++b) {
+      CK(plain_finish(j, l, b, false, &done), "pipeline poll");
+      if (done) {
+        const enterp_status es = plain_issue(j, l, b, off, n);
+        if (es) return es;
+        l.next = off + n;
+        return ENTERP_OK;
+      }
+    }
+  }
+  const int rb = (int)(l.kr & 1);
+  CK(rle_finish(j, l, rb), "run-length wait");  // replicate the chunk issued two run-length steps ago (CPU work)
+  const enterp_status es = rle_issue(j, l, rb, off, n, ls);
+  if (es) return es;
+  ++l.kr;
   l.next = off + n;
-  ++l.k;
   return ENTERP_OK;
 }
 
@@ -895,6 +965,7 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
     const Resolved& rr = c->core->r;
     j.rle = take && !g_no_rle && rr.scalar == ENTERP_F32 && c->pre.empty() && std::isfinite(rr.domain[0]) &&
             std::isfinite(rr.domain[1]) && n_total > (1ull << (24 + RLE_MIN_SHIFT)) && first + count > (1ull << (24 + RLE_MIN_SHIFT));
+    j.hybrid = j.rle && !g_rle_only;
   }
   std::vector<HostLane> lanes((size_t)n_devices);
   enterp_status st = ENTERP_OK;
@@ -924,7 +995,7 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
     more = false;
     for (HostLane& l : lanes) {
       if (!l.hp || l.next >= l.count) continue;
-      st = lane_issue(j, l);
+      st = lane_step(j, l);
       if (st) break;
       more = more || l.next < l.count;
     }
@@ -935,14 +1006,21 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
     if (!l.hp) continue;
     DeviceGuard dg(l.device);
     if (st == ENTERP_OK) {
+      for (int b = 0; b < 2 && st == ENTERP_OK; ++b) {  // CPU work first: the plain copies keep flowing meanwhile
+        const cudaError_t e = rle_finish(j, l, (int)((l.kr + b) & 1));
+        if (e != cudaSuccess) st = cuda_fail(e, "run-length drain");
+      }
       for (int b = 0; b < 2 && st == ENTERP_OK; ++b) {
-        const cudaError_t e = lane_retire(j, l, b);
+        bool done = true;
+        const cudaError_t e = plain_finish(j, l, b, true, &done);
         if (e != cudaSuccess) st = cuda_fail(e, "pipeline drain");
       }
     }
     if (st != ENTERP_OK) {
-      for (int b = 0; b < 2; ++b)
+      for (int b = 0; b < 2; ++b) {
         if (l.hp->stream[b]) cudaStreamSynchronize(l.hp->stream[b]);
+        if (l.hp->rstream[b]) cudaStreamSynchronize(l.hp->rstream[b]);
+      }
     }
     release_pipe(l.hp);
   }
