@@ -172,6 +172,7 @@ struct Replica {
   void* records = nullptr;
   void* slots = nullptr;                // Linear, sorted knots: grid-indexed copies of the interval records (resolve.hpp)
   void* knot_rows = nullptr;
+  void* kslots = nullptr;               // B-splines, sorted knots: grid-indexed copies of the knot rows (resolve.hpp)
   void* pyramid = nullptr;              // all pivot levels, top first, one allocation
   void* buckets = nullptr;              // bucket index of the sorted search (resolve.hpp)
   uint32_t lvl_off[MAX_LEVELS] = {};    // element offsets of the levels inside it
@@ -460,6 +461,7 @@ enterp_status upload_locked(enterp_curve* c, int device, Replica** out) {
   if (r.rec_stride && !g_no_records) want(r.records.data(), r.records.size(), &rp->records);
   if (r.krow_stride && !g_no_records) want(r.knot_rows.data(), r.knot_rows.size(), &rp->knot_rows);
   if (r.n_slots && !g_no_records && !g_no_buckets && !g_no_slots) want(r.slots.data(), r.slots.size(), &rp->slots);
+  if (r.n_kslots && !g_no_records && !g_no_buckets && !g_no_slots) want(r.kslots.data(), r.kslots.size(), &rp->kslots);
   rp->n_lvl = (int)r.levels.level.size();
   std::vector<unsigned char> all;  // the pivot levels, top first, contiguous
   if (rp->n_lvl > 0) {
@@ -546,6 +548,9 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   d.slots = static_cast<const R*>(rp.slots);
   d.n_slots = rp.slots ? r.n_slots : 0;
   d.slot_inv = (R)r.slot_inv;
+  d.kslots = static_cast<const R*>(rp.kslots);
+  d.n_kslots = rp.kslots ? r.n_kslots : 0;
+  d.kslot_inv = (R)r.kslot_inv;
   if (r.n_store > 0) d.k_last = reinterpret_cast<const R*>(r.store.data())[r.ik_off + r.inner_len - 1];
   d.n_lvl = rp.n_lvl;
   for (int l = 0; l < MAX_LEVELS; ++l) {

@@ -8,6 +8,10 @@ template <class R, int DH, bool PROJ, int DEG>
 cudaError_t bspline_pick_knots(bool equi, const CurveDev<R>& c, const SampleSrc<R>& s, R* out, bool vec_ok,
                                cudaStream_t st) {
   if (equi) return launch_grid_stride(bspline_kernel<R, DH, PROJ, DEG, true>, s.count, BLOCK, st, c, s, out, vec_ok);
+  if constexpr (knot_slots_ok<R>(DEG)) {
+    if (c.kslots != nullptr)  // >= 4096 sorted knots: knot-row slots (resolve.hpp)
+      return launch_searching(bspline_slots_kernel<R, DH, PROJ, DEG>, s.count, c.top_bytes, st, c, s, out, vec_ok);
+  }
   return launch_searching(bspline_kernel<R, DH, PROJ, DEG, false>, s.count, c.top_bytes, st, c, s, out, vec_ok);
 }
 

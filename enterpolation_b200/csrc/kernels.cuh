@@ -32,6 +32,9 @@ struct CurveDev {
   uint32_t n_slots;     // grid cells (n_slots + 1 entries)
   R slot_inv;           // cell(x) = clamp(trunc((x - bkt_first) * slot_inv), 0, n_slots - 1)
   R k_last;             // last inner knot
+  const R* kslots;      // B-splines over sorted knots: the knot rows again, indexed by an equal-width grid (resolve.hpp), or nullptr
+  uint32_t n_kslots;    // grid cells (n_kslots + 1 entries); a slot's last value holds its span index as raw bits
+  R kslot_inv;          // cell(x) = clamp(trunc((x - bkt_first) * kslot_inv), 0, n_kslots - 1)
   const R* lvl[MAX_LEVELS];  // 32-ary pivot pyramid, top level first, NaN padded (one contiguous buffer)
   uint32_t lvl_off[MAX_LEVELS];  // offset of each level inside that buffer, in elements
   uint32_t lvl_last[MAX_LEVELS]; // index of the last node of each level
@@ -561,6 +564,10 @@ __device__ __forceinline__ void load_vec(const double* __restrict__ p, double (&
     }
   }
 }
+// span index carried as raw bits in the padding of a knot-row slot
+__device__ __forceinline__ uint32_t raw_index(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ uint32_t raw_index(double v) { return (uint32_t)__double_as_longlong(v); }
+
 // Largest block the generic B-spline kernel may be launched with: 1024 threads (one fat CTA per SM, used
 // when big pivot tables are staged in shared memory) only where the register working set fits the
 // 64-register cap that implies; otherwise 256.
@@ -573,9 +580,22 @@ __host__ __device__ constexpr int bspline_block_cap(int DEG, int DH) {
 // BSpline: span -> gather degree+1 elements and 2*degree knots -> de Boor (bspline/mod.rs:145-169)
 // DEG == 0: runtime degree (DynSpace semantics; workspace in local memory).
 // =================================================================================================
-template <class R, int DH, bool PROJ, int DEG, bool EQUI>
-__global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(const CurveDev<R> c, const SampleSrc<R> s, R* __restrict__ out,
-                                                        const bool vec_ok) {
+// SLOTS: the knot-row slot variant (sorted knots, degrees 1..3 whose rows have padding to spare). A separate
+// instantiation: the extra live row costs registers that the plain variant must not pay.
+template <class R>
+__host__ __device__ constexpr int knot_row_stride(int deg) {
+  return (2 * deg + (32 / (int)sizeof(R)) - 1) / (32 / (int)sizeof(R)) * (32 / (int)sizeof(R));
+}
+template <class R>
+__host__ __device__ constexpr bool knot_slots_ok(int deg) {
+  // f32 only: a whole slot is ONE 32-byte sector there. For f64 (64-byte rows) the variant measured slower than the
+  // bucket index on C4 (27.0 vs 32.7 G samples/s: 40 bytes of spills at the 3-CTA register cap, or 2 CTAs without it).
+  return sizeof(R) == 4 && deg >= 1 && deg <= 3 && 2 * deg < knot_row_stride<R>(deg);
+}
+
+template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool SLOTS>
+__device__ __forceinline__ void bspline_body(const CurveDev<R>& c, const SampleSrc<R>& s, R* __restrict__ out, const bool vec_ok) {
+  static_assert(!SLOTS || (!EQUI && knot_slots_ok<R>(DEG)), "slot variant: sorted knots, rows with padding");
   constexpr int P_CAP = DEG > 0 ? DEG : MAX_DYN_DEGREE;
   const int p = DEG > 0 ? DEG : (int)c.degree;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -589,19 +609,45 @@ __global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(
     const bool active = i < s.count;
     const bool full_warp = base + (threadIdx.x | 31u) < s.count;
     R x = active ? apply_pre(c, sample_param(s, i)) : c.eq_first;
-    uint32_t index;
-    bool valid = bspline_span<R, EQUI>(c, x, index, top);
+    uint32_t index = 0;
+    bool valid = true;
+    // knot-row stride of the compile-time degrees: 2 * degree knots padded to whole 32-byte sectors
+    constexpr int KSTR = (2 * P_CAP + (32 / (int)sizeof(R)) - 1) / (32 / (int)sizeof(R)) * (32 / (int)sizeof(R));
+    R kr[DEG > 0 ? KSTR : 1];
+    bool have_row = false;
+    if constexpr (SLOTS) {
+      // Knot-row slots (resolve.hpp; the Linear slot table's idea, linear_slots_kernel): cell(x) is monotone, so slot
+      // b (the span whose upper knot is the first knot of cell b or beyond) serves x unless x has passed that knot;
+      // slot b + 1 (the span whose lower knot is the last knot of cell b) serves it if x has passed that one too.
+      // The row brings its span index along, so the bucket-index gather disappears for ~97 % of the samples (C4:
+      // 7.16 -> 6.5 missing sectors per sample on the L1 -> XBAR port that bounds this kernel).
+      {
+        const R tq = xmul(xsub(x, c.bkt_first), c.kslot_inv);
+        const uint32_t b = min(tq >= R(0) ? bucket_sat_u32(tq) : 0u, c.n_kslots - 1u);
+        if (b != 0u) {
+          load_vec<KSTR, true>(c.kslots + (size_t)b * KSTR, kr);
+          have_row = !(x >= kr[DEG]);  // kr[p] = knots[index]
+          if (!have_row) {
+            load_vec<KSTR, true>(c.kslots + (size_t)(b + 1u) * KSTR, kr);
+            have_row = x >= kr[DEG - 1];  // kr[p - 1] = knots[index - 1]
+          }
+          if (have_row) index = raw_index(kr[KSTR - 1]);
+        }
+      }
+    }
+    if (!have_row) valid = bspline_span<R, EQUI>(c, x, index, top);
     if (!active) continue;
     const uint32_t first = index - (uint32_t)p;
     R kn[2 * P_CAP];
     R ws[(P_CAP + 1) * DH];
     const R* __restrict__ vk = c.vk + first;
     const R* __restrict__ el = c.elems + (size_t)first * DH;
-    if (DEG > 0) {
+    if constexpr (DEG > 0) {
       // gathers: vector loads (LDG.E.256 / .128) where the layout guarantees alignment
-      constexpr int KSTR = (2 * P_CAP + (32 / (int)sizeof(R)) - 1) / (32 / (int)sizeof(R)) * (32 / (int)sizeof(R));
-      if (c.knot_rows != nullptr) {
-        R kr[KSTR];
+      if (have_row) {
+#pragma unroll
+        for (int m = 0; m < 2 * P_CAP; ++m) kn[m] = kr[m];
+      } else if (c.knot_rows != nullptr) {
         load_vec<KSTR, true>(c.knot_rows + (size_t)(index - c.krow_lo) * KSTR, kr);
 #pragma unroll
         for (int m = 0; m < 2 * P_CAP; ++m) kn[m] = kr[m];
@@ -645,6 +691,17 @@ __global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(
     }
     finish_and_store<R, DH, PROJ>(out, i, ws, valid, vec_ok, c.invalid, stage, full_warp);
   }
+}
+
+template <class R, int DH, bool PROJ, int DEG, bool EQUI>
+__global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH)) bspline_kernel(const CurveDev<R> c, const SampleSrc<R> s, R* __restrict__ out,
+                                                        const bool vec_ok) {
+  bspline_body<R, DH, PROJ, DEG, EQUI, false>(c, s, out, vec_ok);
+}
+template <class R, int DH, bool PROJ, int DEG>
+__global__ void __launch_bounds__(bspline_block_cap<R>(DEG, DH), 3) bspline_slots_kernel(const CurveDev<R> c, const SampleSrc<R> s,
+                                                                                         R* __restrict__ out, const bool vec_ok) {
+  bspline_body<R, DH, PROJ, DEG, false, true>(c, s, out, vec_ok);
 }
 
 // record stride (in R) of the Linear interval table for DH components — must match resolve.cpp

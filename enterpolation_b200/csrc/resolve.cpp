@@ -672,6 +672,44 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
       r.krow_stride = stride;
       r.knot_rows.resize(kr.size() * sizeof(R));
       std::memcpy(r.knot_rows.data(), kr.data(), r.knot_rows.size());
+      // knot-row slots (resolve.hpp): cell(x) -> the row (and span index) that serves x, or its neighbour
+      const uint64_t n_s = r.imax - r.imin;  // searched knots
+      const bool map_simple = (r.imin > 0 && r.imax < s.inner_len) || s.adaptor == AD_NONE;
+      uint64_t per_knot = 2;
+      if (const char* e = std::getenv("ENTERP_SLOTS_PER_KNOT")) {
+        const long v = std::atol(e);
+        if (v >= 0 && v <= 16) per_knot = (uint64_t)v;
+      }
+      if (d.knot_base == ENTERP_KNOTS_SORTED && per_knot > 0 && n_s >= 4096 && sizeof(R) == 4 && s.degree <= 3 && 2 * s.degree < stride && map_simple &&
+          !r.buckets.empty()) {
+        const R* sk = inner.data() + r.imin;
+        const R first = sk[0], last = sk[n_s - 1];
+        uint64_t ns = 1;
+        while (ns < per_knot * n_s) ns <<= 1;
+        const R inv = (R)ns / (last - first);
+        if ((ns + 1) * stride * sizeof(R) <= (64ull << 20) + stride * sizeof(R) && last > first && std::isfinite(inv) && inv > R(0)) {
+          std::vector<R> sl((size_t)(ns + 1) * stride);
+          uint64_t pcount = 0;  // searched knots whose cell is below b
+          for (uint64_t b = 0; b <= ns; ++b) {
+            while (b < ns && pcount < n_s && bucket_of<R>(sk[pcount], first, inv, (uint32_t)ns) < b) ++pcount;
+            if (b == ns) pcount = n_s;
+            const uint64_t index = (uint64_t)((int64_t)(r.imin + pcount) + r.map_add);  // span index, in [lo, hi]
+            R* dst = sl.data() + b * stride;
+            std::memcpy(dst, kr.data() + (index - lo) * stride, stride * sizeof(R));
+            const uint32_t bits = (uint32_t)index;
+            if (sizeof(R) == 4) {
+              std::memcpy(dst + stride - 1, &bits, 4);
+            } else {
+              const uint64_t wide = bits;
+              std::memcpy(dst + stride - 1, &wide, 8);
+            }
+          }
+          r.n_kslots = (uint32_t)ns;
+          r.kslot_inv = inv;
+          r.kslots.resize(sl.size() * sizeof(R));
+          std::memcpy(r.kslots.data(), sl.data(), r.kslots.size());
+        }
+      }
     }
   }
   if (d.kind == ENTERP_LINEAR && d.knot_base == ENTERP_KNOTS_SORTED && s.inner_len >= 2) {

@@ -76,6 +76,12 @@ struct Resolved {
   std::vector<unsigned char> slots;
   uint32_t n_slots = 0;
   double slot_inv = 0;
+  // B-splines over >= 4096 sorted knots, generic kernel: the knot rows again, indexed by the same kind of grid (2 cells
+  // per searched knot): slot b = knot row of span imin + P_b (+ map_add), its last (padding) value carrying that span
+  // index as raw bits. Only where a row has padding to spare (2 * degree < krow_stride).
+  std::vector<unsigned char> kslots;
+  uint32_t n_kslots = 0;
+  double kslot_inv = 0;
   // Linear easing (easing/mod.rs:86-132, plateau.rs): kind, N of smoothstart/smoothend, Plateau min/max in R
   int32_t easing = 0, easing_n = 0;
   double ease_min = 0, ease_max = 1;

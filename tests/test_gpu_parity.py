@@ -941,3 +941,29 @@ def test_take_host_run_length_transfer(dim):
     lib.enterp_host_transfer_bytes(None, C.byref(d1))
     assert_bits_equal(got, ref.clamp().take(n_total, first, count, threads=8), "clamped curve, plain transfer")
     assert d1.value - d0.value == count * dim * 4
+
+
+@pytest.mark.parametrize("degree", [1, 2, 3])
+@pytest.mark.parametrize("mode", ["open", "clamped", "legacy"])
+def test_bspline_knot_row_slots(degree, mode):
+    """f32 B-splines over >= 4096 sorted knots, degrees 1..3: the generic kernel finds span and knot row through the
+    grid-indexed knot-row slots (bspline_slots_kernel). Every knot, its float neighbours, out of domain, NaN/inf; knots
+    with repeats and a cluster; all three builder modes (the span index a slot carries includes the adaptor's shift)."""
+    rng = np.random.default_rng(degree * 7 + len(mode))
+    n_k = 5000
+    k = np.cumsum(0.5 + u01(n_k, 0xB1 + degree, np.float64))
+    k[1000:1040] = k[1000] + np.arange(40) * 1e-3      # a cluster that overflows its cell
+    k[2000:2003] = k[2000]                              # repeated interior knots
+    k = np.sort(k).astype(np.float32)
+    if mode == "open":
+        e = n_k - degree + 1
+        b = BSpline.builder().elements(rand_elements(e, 3, np.float32, 0xB5)).knots(k).constant(degree + 1)
+    elif mode == "clamped":
+        e = n_k + degree - 1
+        b = BSpline.builder().clamped().elements(rand_elements(e, 3, np.float32, 0xB6)).knots(k).constant(degree + 1)
+    else:
+        e = n_k - degree - 1
+        b = BSpline.builder().legacy().elements(rand_elements(e, 3, np.float32, 0xB7)).knots(k).constant(degree + 1)
+    t = adversarial(k, np.float32, rng, n_random=20000)
+    t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf], dtype=np.float32)])
+    check_curve(b, t, what=f"knot-row slots degree {degree} {mode}")
