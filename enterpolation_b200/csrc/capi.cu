@@ -110,6 +110,13 @@ static const bool g_no_slots = [] {
   return v && v[0] == '1';
 }();
 
+// Ablation switch (env ENTERP_BALLOT_SEARCH=1): sorted searches through the warp-cooperative ballot/shuffle 32-ary
+// search of the north star (kernels.cuh count_le_ballot) instead of bucket index / records / slots / pivot tree.
+static const bool g_ballot_search = [] {
+  const char* v = std::getenv("ENTERP_BALLOT_SEARCH");
+  return v && v[0] == '1';
+}();
+
 // Ablation switch (env ENTERP_NO_SMEM_PIVOTS=1): leave every pivot level in global memory / L1.
 static const bool g_no_smem_pivots = [] {
   const char* v = std::getenv("ENTERP_NO_SMEM_PIVOTS");
@@ -580,6 +587,15 @@ CurveDev<R> make_dev(const enterp_curve& cv, const Replica& rp) {
   d.eq_const = r.knot_base == ENTERP_KNOTS_CONST_EQUIDISTANT ? 1 : 0;
   d.eq_mode = r.eq_mode;
   d.eq_rstep = (R)r.eq_rstep;
+  if (g_ballot_search && r.knot_base == ENTERP_KNOTS_SORTED) {
+    d.ballot = 1;  // every structure in front of the plain knot array is switched off
+    d.records = nullptr;
+    d.slots = nullptr;
+    d.kslots = nullptr;
+    d.bkt = nullptr;
+    d.top_bytes = 0;
+    d.n_top = 0;
+  }
   d.n_pre = (int)cv.pre.size();
   for (int i = 0; i < d.n_pre && i < MAX_PRE; ++i) {
     d.pre_kind[i] = cv.pre[i].kind;
@@ -636,7 +652,7 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
       // equidistant knots a span division the kernel can do exactly without the IEEE divide.
       const bool map_simple = (r.imin > 0 && r.imax < r.inner_len) || r.adaptor == AD_NONE;
       const bool eq_ok = !equi || (r.rows_mode == 1 ? r.eq_mode == 1 : r.eq_mode >= 1);
-      if (r.rows_mode && rp.rows && deg > 0 && vec_ok && map_simple && eq_ok && !g_disable_rows) {
+      if (r.rows_mode && rp.rows && deg > 0 && vec_ok && map_simple && eq_ok && !g_disable_rows && !g_ballot_search) {
         RowsDev<R> rw{};
         rw.table = static_cast<const R*>(rp.rows);
         rw.n_rows = r.rows_n;
@@ -655,7 +671,7 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
       break;
     }
     case ENTERP_LINEAR:
-      if (!g_disable_lean && lean_linear<R>(r.dh, proj, equi, d, s, static_cast<R*>(out), vec_ok, st, &e)) break;
+      if (!g_disable_lean && !g_ballot_search && lean_linear<R>(r.dh, proj, equi, d, s, static_cast<R*>(out), vec_ok, st, &e)) break;
       e = launch_linear<R>(r.dh, proj, equi, d, s, static_cast<R*>(out), vec_ok, st);
       break;
     default: {

@@ -45,6 +45,7 @@ struct CurveDev {
   const uint32_t* bkt;
   uint32_t n_bkt;
   R bkt_first, bkt_inv;
+  int ballot;  // ablation (ENTERP_BALLOT_SEARCH=1): the warp-cooperative ballot/shuffle 32-ary search instead of index/tree
   uint32_t n_elem, inner_len, virt_len, degree;
   uint32_t imin, imax, map0, mapL;
   int32_t map_add;
@@ -333,8 +334,40 @@ __device__ __forceinline__ bool bucket_lookup(const CurveDev<R>& c, R x, uint32_
   return w.w == 0u;
 }
 
+// Ablation (ENTERP_BALLOT_SEARCH=1): the warp-cooperative 32-ary search BASELINE.json's north star names. The warp
+// serves its 32 samples one after the other: sample j's parameter is broadcast by shuffle, every lane probes one of 32
+// equidistant pivots of the current range, a ballot narrows the range 32-fold (4 rounds for 2^20 knots). It costs a
+// gather instruction per round PER SAMPLE where the per-thread searches cost one per round per WARP, which is why it
+// is not the product path (C2: profiles/r02_ncu_c2_ballot_search.txt). Must be called by all 32 lanes.
+template <class R>
+__device__ __noinline__ uint32_t count_le_ballot(const R* __restrict__ k, uint32_t n, R x) {
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t mine = 0;
+  for (int j = 0; j < 32; ++j) {
+    const R xj = __shfl_sync(0xFFFFFFFFu, x, j);
+    uint32_t lo = 0, len = n, result = 0;
+    for (;;) {
+      if (len <= 32u) {
+        const bool le = lane < len && __ldg(k + lo + lane) <= xj;
+        result = lo + __popc(__ballot_sync(0xFFFFFFFFu, le));
+        break;
+      }
+      const uint32_t step = (len + 31u) / 32u;
+      const uint32_t end = min(len, (lane + 1u) * step);          // this lane's block is [lane * step, end)
+      const bool le = lane * step < len && __ldg(k + lo + end - 1u) <= xj;
+      const uint32_t t = __popc(__ballot_sync(0xFFFFFFFFu, le));  // blocks whose last knot is <= x: a prefix (sorted knots)
+      const uint32_t skip = min(len, t * step);
+      lo += skip;
+      len = min(step, len - skip);
+    }
+    if ((int)lane == j) mine = result;
+  }
+  return mine;
+}
+
 template <class R>
 __device__ __forceinline__ uint32_t count_le(const CurveDev<R>& c, R x, const R* __restrict__ top = nullptr) {
+  if (c.ballot) return count_le_ballot<R>(c.ik + c.imin, c.imax - c.imin, x);
   uint32_t lo, hi;
   if (!bucket_lookup(c, x, lo, hi)) return count_le_tree(c, x, top);  // one call site: the unrolled descent is big
   hi += lo;
