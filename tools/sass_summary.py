@@ -17,7 +17,10 @@ KERNELS = [
     ("C5 256 stops, stepper runs (VARIANT 4)", r"bspline_rows_kernelIfLi4ELb0ELi3ELb1ELb0ELi4E"),
     ("C5-like random batch (VARIANT 0)", r"bspline_rows_kernelIfLi4ELb0ELi3ELb1ELb1ELi0E"),
     ("C1 f64 take (VARIANT 3)", r"bspline_rows_kernelIdLi1ELb0ELi3ELb1ELb0ELi3E"),
-    ("C2 Linear [f32;3] sorted batch", r"linear_kernelIfLi3ELb0ELb0E"),
+    ("C2 Linear [f32;3] sorted batch, slot table (linear_slots_kernel)", r"linear_slots_kernelIfLi3ELb0E"),
+    ("C2 fallback: Linear [f32;3] sorted batch, bucket index + records", r"linear_kernelIfLi3ELb0ELb0E"),
+    ("cubic [f32;4] B-spline over sorted knots, knot-row slots", r"bspline_slots_kernelIfLi4ELb0ELi3E"),
+    ("run-length host transfer: stepper values at representable indices", r"stepper_strided_kernelIfE"),
     ("C3 bezier_many [f32;3] x 16", r"bezier_many_kernelIfLi3ELi16E"),
     ("C4 NURBS f64 generic", r"bspline_kernelIdLi4ELb1ELi3ELb0E"),
 ]
