@@ -931,6 +931,19 @@ def test_take_host_run_length_transfer(dim):
         st = lib.enterp_take_host_multi(curve._h, arr, len(devices), n_total, first, count, pinned.data_ptr())
         assert st == 0
         assert_bits_equal(pinned.numpy(), want, f"rle take_host_multi dim {dim} pinned")
+    # the other curve kinds go through the same transfer (their batch kernels evaluate the distinct values)
+    others = [Linear.builder().elements(rand_elements(40, dim, np.float32, 0xA5)).equidistant("f32").normalized(),
+              Linear.builder().elements(rand_elements(40, dim, np.float32, 0xA6)).knots(sorted_knots(40, np.float32, 0xA7)),
+              Bezier.builder().elements(rand_elements(6, dim, np.float32, 0xA8)).normalized("f32").constant()]
+    if dim > 1:
+        w = (u01(30, 0xA9, np.float32) + np.float32(0.5)).astype(np.float32)
+        others.append(BSpline.builder().elements_with_weights(rand_elements(30, dim, np.float32, 0xAA), w)
+                      .knots(sorted_knots(32, np.float32, 0xAB)).constant(4))
+    for ob in others:
+        oc, oref = ob.build(), oracle.OracleCurve(ob.to_desc())
+        n_total, first, count = n32, 3 * (1 << 30) - 70_000, (1 << 22) + 140_001
+        assert_bits_equal(Take(oc, n_total, first, count).collect(), oref.take(n_total, first, count, threads=8),
+                          f"rle take_host, other kinds, dim {dim}")
     # adaptors switch the run-length transfer off (a mapped parameter could leave the valid range): still exact
     cl = curve.clamp()
     n_total, first, count = n32, (1 << 30) + 5, 300_001
