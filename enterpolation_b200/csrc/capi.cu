@@ -638,6 +638,18 @@ SampleSrc<R> batch_src(const void* t, uint64_t n) {
 template <class R>
 enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const SampleSrc<R>& s, void* out, cudaStream_t st) {
   const Resolved& r = cv.core->r;
+  // The lean Linear / Bezier take kernels index with 32 bits and stop at 2^32 - 2^24 (inst_lean.cuh): a take that
+  // crosses that index (take(2^32) itself) is cut there, so that all but its last 2^24 samples keep the lean kernel
+  constexpr uint64_t LEAN_SPLIT = (1ull << 32) - (1ull << 24);
+  if (s.t == nullptr && r.kind != ENTERP_BSPLINE && !g_disable_lean && s.first < LEAN_SPLIT && s.count > LEAN_SPLIT - s.first) {
+    SampleSrc<R> a = s, b = s;
+    a.count = LEAN_SPLIT - s.first;
+    b.first = LEAN_SPLIT;
+    b.count = s.count - a.count;
+    const enterp_status sa = dispatch_eval<R>(cv, rp, a, out, st);
+    if (sa) return sa;
+    return dispatch_eval<R>(cv, rp, b, static_cast<R*>(out) + a.count * (uint64_t)r.dim, st);
+  }
   const CurveDev<R> d = make_dev<R>(cv, rp);
   const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 16u) == 0;
   const bool proj = r.weighted != 0;

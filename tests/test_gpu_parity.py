@@ -980,3 +980,20 @@ def test_bspline_knot_row_slots(degree, mode):
     t = adversarial(k, np.float32, rng, n_random=20000)
     t = np.concatenate([t, np.array([np.nan, np.inf, -np.inf], dtype=np.float32)])
     check_curve(b, t, what=f"knot-row slots degree {degree} {mode}")
+
+
+def test_linear_and_bezier_takes_across_the_lean_index_limit():
+    """The lean Linear / Bezier take kernels index with 32 bits up to 2^32 - 2^24; a take that crosses that index is cut
+    there (capi.cu dispatch_eval) instead of leaving the whole call to the generic kernels."""
+    lim = (1 << 32) - (1 << 24)
+    builders = [Linear.builder().elements(rand_elements(64, 4, np.float32, 0xC1)).equidistant("f32").normalized(),
+                Linear.builder().elements(rand_elements(64, 3, np.float64, 0xC2)).knots(sorted_knots(64, np.float64, 0xC3)),
+                Bezier.builder().elements(rand_elements(4, 4, np.float32, 0xC4)).normalized("f32").constant()]
+    lib = _abi.load_library()
+    for b in builders:
+        c, ref = b.build(), oracle.OracleCurve(b.to_desc())
+        for n_total, first, count in (((1 << 32), lim - 5000, 10001), ((1 << 33) + 5, lim - 1, 4097), ((1 << 32), lim, 3000)):
+            before = lib.enterp_launch_count()
+            got = c.take_device(n_total, first, count).cpu().numpy()
+            assert lib.enterp_launch_count() - before == (2 if first < lim else 1)
+            assert_bits_equal(got, ref.take(n_total, first, count), f"take({n_total}) [{first}, +{count})")

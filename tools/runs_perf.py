@@ -25,6 +25,13 @@ def main():
     el = bench.u01(256 * 4, 0xE1, np.float32).reshape(256, 4)
     c = BSpline.builder().elements(el).knots(k).constant(4).build()
     timeit(lambda: c.take_device(n, out=out), n, f"[{tag}] sorted cubic 256 take(2^{log2n})", 16)
+    # Linear / Bezier takes of the same size (lean kernels up to index 2^32 - 2^24, the generic ones beyond)
+    from enterpolation_b200 import Bezier, Linear
+    el64 = bench.u01(64 * 4, 1, np.float32).reshape(64, 4)
+    c = Linear.builder().elements(el64).equidistant("f32").normalized().build()
+    timeit(lambda: c.take_device(n, out=out), n, f"[{tag}] Linear 64 stops [f32;4] take(2^{log2n})", 16)
+    c = Bezier.builder().elements(el64[:4]).normalized("f32").constant().build()
+    timeit(lambda: c.take_device(n, out=out), n, f"[{tag}] cubic Bezier [f32;4] take(2^{log2n})", 16)
     # shard sizes of the 8-GPU run
     c = bench.gradient_builder(5).build()
     m = n // 8
