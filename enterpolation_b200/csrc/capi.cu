@@ -2,6 +2,7 @@
 // dispatch, and the host-buffer pipelines. No CPU evaluation path exists in this file or anywhere
 // in the library: every eval entry point ends in a kernel launch or an error status.
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <functional>
@@ -284,8 +285,11 @@ class FillPool {
     static FillPool* p = new FillPool();  // lives until process exit
     return *p;
   }
-  // fn(lo, hi) over [0, total) in blocks of `block`; the caller works too. One run at a time.
-  void run(uint64_t total, uint64_t block, const std::function<void(uint64_t, uint64_t)>& fn) {
+  // fn(lo, hi) over [0, total) in blocks of `block`; the caller works too. One run at a time. `between` (may be
+  // empty) is called by the CALLING thread after every block it fills and while it waits for the workers: the host
+  // pipeline uses it to keep the copy engine fed during a fill.
+  void run(uint64_t total, uint64_t block, const std::function<void(uint64_t, uint64_t)>& fn,
+           const std::function<void()>& between = std::function<void()>()) {
     std::lock_guard<std::mutex> serial(run_mu_);
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -297,9 +301,20 @@ class FillPool {
       ++gen_;
     }
     cv_.notify_all();
-    work();
+    for (;;) {
+      const uint64_t lo = next_.fetch_add(block_, std::memory_order_relaxed);
+      if (lo >= total_) break;
+      fn(lo, lo + block_ < total_ ? lo + block_ : total_);
+      if (between) between();
+    }
     std::unique_lock<std::mutex> lk(mu_);
-    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    while (!done_cv_.wait_for(lk, std::chrono::microseconds(50), [&] { return pending_ == 0; })) {
+      if (between) {
+        lk.unlock();
+        between();
+        lk.lock();
+      }
+    }
     fn_ = nullptr;
   }
 
@@ -783,6 +798,7 @@ struct HostLane {
   Replica* rp = nullptr;
   HostPipe* hp = nullptr;
   uint64_t off0 = 0, count = 0, chunk = 0, next = 0, k = 0, kr = 0;
+  enterp_status err = ENTERP_OK;  // first failure of a chunk issued from inside a host fill (j.feed)
   struct Pending {
     bool live = false;
     uint64_t off = 0, n = 0;
@@ -801,6 +817,7 @@ struct HostJob {
   bool pin_in, pin_out;
   bool rle;     // f32 take of a curve without input adaptors over a finite domain: chunks beyond 2^26 may ship runs only
   bool hybrid;  // ... and the copy engine takes plain chunks beside them
+  std::function<void()> feed;  // hands every idle plain slot (of every lane) its next chunk; called during host fills
 };
 
 constexpr unsigned RLE_MIN_SHIFT = 2;  // runs of at least 4 samples (indices from 2^26 on)
@@ -855,10 +872,10 @@ cudaError_t rle_finish(const HostJob& j, HostLane& l, int b) {
   unsigned char* dst = static_cast<unsigned char*>(j.out_host) + (l.off0 + pd.off) * j.out_stride;
   const unsigned char* vals = static_cast<const unsigned char*>(l.hp->rle_stage[b].p);
   const size_t stride = j.out_stride;
-  FillPool::get().run(pd.n, 1u << 16, [&](uint64_t lo, uint64_t hi) {
-    expand_runs_any(stride, dst + lo * stride, vals, a + lo, a + hi, pd.vb, pd.ls);
-  });
   l.rpend[b].live = false;
+  FillPool::get().run(
+      pd.n, 1u << 16,
+      [&](uint64_t lo, uint64_t hi) { expand_runs_any(stride, dst + lo * stride, vals, a + lo, a + hi, pd.vb, pd.ls); }, j.feed);
   return cudaSuccess;
 }
 
@@ -929,6 +946,26 @@ enterp_status rle_issue(const HostJob& j, HostLane& l, int b, uint64_t off, uint
   return ENTERP_OK;
 }
 
+// Hands the lane's next chunk to the copy engine if one of its plain slots is free (non-blocking).
+enterp_status feed_lane(const HostJob& j, HostLane& l) {
+  if (!l.hp || l.next >= l.count) return ENTERP_OK;
+  DeviceGuard g(l.device);
+  if (!g.ok) return ENTERP_NO_DEVICE;
+  for (int b = 0; b < 2; ++b) {
+    bool done = true;
+    CK(plain_finish(j, l, b, false, &done), "pipeline poll");
+    if (done) {
+      const uint64_t off = l.next;
+      const uint64_t n = l.count - off < l.chunk ? l.count - off : l.chunk;
+      const enterp_status es = plain_issue(j, l, b, off, n);
+      if (es) return es;
+      l.next = off + n;
+      return ENTERP_OK;
+    }
+  }
+  return ENTERP_OK;
+}
+
 // One unit of work for the lane: claims its next chunk for the copy engine or for the CPU path (see HostLane).
 enterp_status lane_step(const HostJob& j, HostLane& l) {
   DeviceGuard g(l.device);
@@ -948,22 +985,24 @@ enterp_status lane_step(const HostJob& j, HostLane& l) {
     return ENTERP_OK;
   }
   if (j.hybrid) {  // a free plain slot means an idle copy engine: feed it first
-    for (int b = 0; b < 2; ++b) {
-      CK(plain_finish(j, l, b, false, &done), "pipeline poll");
-      if (done) {
-        const enterp_status es = plain_issue(j, l, b, off, n);
-        if (es) return es;
-        l.next = off + n;
-        return ENTERP_OK;
-      }
-    }
+    const uint64_t before = l.next;
+    const enterp_status es = feed_lane(j, l);
+    if (es) return es;
+    if (l.next != before) return ENTERP_OK;
   }
   const int rb = (int)(l.kr & 1);
-  CK(rle_finish(j, l, rb), "run-length wait");  // replicate the chunk issued two run-length steps ago (CPU work)
-  const enterp_status es = rle_issue(j, l, rb, off, n, ls);
+  // replicate the chunk issued two run-length steps ago (CPU work; j.feed keeps the copy engine busy meanwhile and
+  // may claim chunks, so the next chunk is looked at again afterwards)
+  CK(rle_finish(j, l, rb), "run-length wait");
+  if (l.err) return l.err;
+  if (l.next >= l.count) return ENTERP_OK;
+  const uint64_t off2 = l.next;
+  const uint64_t n2 = l.count - off2 < l.chunk ? l.count - off2 : l.chunk;
+  if (!rle_eligible(j, j.first + l.off0 + off2, n2, &ls)) return ENTERP_OK;  // the next lane_step takes it as a plain chunk
+  const enterp_status es = rle_issue(j, l, rb, off2, n2, ls);
   if (es) return es;
   ++l.kr;
-  l.next = off + n;
+  l.next = off2 + n2;
   return ENTERP_OK;
 }
 
@@ -1022,6 +1061,11 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
     const cudaError_t e = lane_prepare(j, l);
     if (e != cudaSuccess) st = cuda_fail(e, "host pipeline scratch");
   }
+  if (j.hybrid)
+    j.feed = [&j, &lanes]() {
+      for (HostLane& fl : lanes)
+        if (fl.err == ENTERP_OK) fl.err = feed_lane(j, fl);
+    };
   // round-robin issue: every device gets its next chunk before anyone gets a second one
   bool more = st == ENTERP_OK;
   while (more) {
@@ -1029,6 +1073,7 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
     for (HostLane& l : lanes) {
       if (!l.hp || l.next >= l.count) continue;
       st = lane_step(j, l);
+      if (st == ENTERP_OK) st = l.err;
       if (st) break;
       more = more || l.next < l.count;
     }
@@ -1042,6 +1087,7 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
       for (int b = 0; b < 2 && st == ENTERP_OK; ++b) {  // CPU work first: the plain copies keep flowing meanwhile
         const cudaError_t e = rle_finish(j, l, (int)((l.kr + b) & 1));
         if (e != cudaSuccess) st = cuda_fail(e, "run-length drain");
+        if (st == ENTERP_OK) st = l.err;
       }
       for (int b = 0; b < 2 && st == ENTERP_OK; ++b) {
         bool done = true;
