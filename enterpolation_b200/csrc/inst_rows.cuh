@@ -88,7 +88,7 @@ cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
   if constexpr (sizeof(R) == 4) {
     constexpr unsigned long long RUN0 = 1ull << 24;
     const unsigned long long end = s.first + s.count;
-    if (s.t == nullptr && !need_check && !rows_no_runs() && end >= RUN0 + 4096 && end < (1ull << 62)) {
+    if (s.t == nullptr && !rows_no_runs() && end >= RUN0 + 4096 && end < (1ull << 62)) {
       const unsigned long long split = s.first > RUN0 ? s.first : RUN0;
       constexpr int D = PROJ ? DH - 1 : DH;
       if (split > s.first) {
@@ -100,6 +100,8 @@ cudaError_t rows_launch_one(const CurveDev<R>& c, const SampleSrc<R>& s, R* out,
       SampleSrc<R> tail = s;
       tail.first = split;
       tail.count = end - split;
+      if (need_check)  // input adaptors / possible panics
+        return rows_launch_runs(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 6>, c, tail, out + (split - s.first) * D, rw, st);
       return rows_launch_runs(bspline_rows_kernel<R, DH, PROJ, DEG, EQUI, POW2, 4>, c, tail, out + (split - s.first) * D, rw, st);
     }
   }

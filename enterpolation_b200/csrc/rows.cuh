@@ -399,9 +399,13 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
   // RN-even(i / 2^ls), which is what from_usize(i) rounds to, computed in integers. Bit-exact by construction
   // (same t, same arithmetic), ~1/2^ls of the FP work, and the kernel runs at the store roof.
   if constexpr (RUNS) {
-    static_assert(sizeof(R) == 4 && TAKE && !CHECK && !CHUNK, "f32 check-free take only");
+    static_assert(sizeof(R) == 4 && TAKE && !CHUNK, "f32 takes only");
     constexpr int NV = BLOCK;
     __shared__ __align__(16) R vals[2][(NV + 1) * D];
+    // CHECK (input adaptors, possible panics): a value the reference would panic on is NaN for every sample of its
+    // run, and the invalid counter advances by the run's samples inside this launch, as the per-sample kernels count
+    __shared__ unsigned char bad[CHECK ? 2 : 1][CHECK ? NV + 1 : 1];
+    unsigned long long n_bad = 0;
     const unsigned lt = rw.runs_lt;
     const unsigned long long A = s.first, B = s.first + s.count;
     const unsigned long long tile1 = (B - 1) >> lt;
@@ -418,13 +422,14 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
         R* __restrict__ vbuf = vals[buf];
         for (uint32_t m = threadIdx.x; m < nvals; m += BLOCK) {
           const unsigned long long v = vb + ((unsigned long long)m << ls);
-          const R x = xadd(xmul(s.step, from_index(v, R(0))), s.start);  // from_index(v) is exact
+          const R x = pre_only(xadd(xmul(s.step, from_index(v, R(0))), s.start));  // from_index(v) is exact
           bool valid;
-          const uint32_t ri = rows_span<R, EQUI, POW2, false>(c, rw, x, valid);
+          const uint32_t ri = rows_span<R, EQUI, POW2, CHECK>(c, rw, x, valid);
           eval_to(x, true, ri, [&](const R(&v4)[D]) {
 #pragma unroll
-            for (int q = 0; q < D; ++q) vbuf[m * D + q] = v4[q];
+            for (int q = 0; q < D; ++q) vbuf[m * D + q] = (CHECK && !valid) ? qnan(R(0)) : v4[q];
           });
+          if (CHECK) bad[CHECK ? buf : 0][CHECK ? m : 0] = valid ? 0 : 1;
         }
         __syncthreads();  // one barrier per sub-tile: the other buffer is free once everybody has passed this one
         const unsigned long long lo_i = sb > A ? sb : A;
@@ -442,6 +447,7 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
           for (; dd < end; dd += (U)BLOCK, dst += (size_t)BLOCK * D) {
             const U par = ((dd >> ls) + vpar) & (U)1;
             const uint32_t m = (uint32_t)((dd + hm1 + par) >> ls);
+            if (CHECK) n_bad += bad[CHECK ? buf : 0][CHECK ? m : 0];
             R v4[D];
             if constexpr (D == 4) {
               const float4 t4 = reinterpret_cast<const float4*>(vbuf)[m];
@@ -460,6 +466,7 @@ __device__ __forceinline__ void rows_body(const CurveDev<R>& c, const SampleSrc<
         buf ^= 1;
       }
     }
+    if (CHECK && n_bad) atomicAdd(c.invalid, n_bad);
     return;
   }
 
@@ -525,14 +532,17 @@ __host__ __device__ constexpr int rows_min_blocks(int P, int DH, bool POW2) {
 // reference accepts is an interval unbounded below, so it suffices that both ends of the launch's range
 // are valid), 3 = take, check-free, CHUNKed, rows read from global memory (any table size; sorted knots skip
 // the search while a thread stays in its span), 4 = f32 take beyond index 2^24, check-free: one evaluation per
-// distinct stepper value, broadcast through shared memory (RUNS above). Separate kernels rather than paths in one:
+// distinct stepper value, broadcast through shared memory (RUNS above), 6 = the same with input adaptors and the
+// per-sample panic accounting. Separate kernels rather than paths in one:
 // the hot loop is I-cache sensitive.
 template <class R, int DH, bool PROJ, int DEG, bool EQUI, bool POW2, int VARIANT>
 __global__ void __launch_bounds__(BLOCK, rows_min_blocks<R>(DEG, DH, POW2)) bspline_rows_kernel(const CurveDev<R> c,
                                                                                                const SampleSrc<R> s,
                                                                                                R* __restrict__ out,
                                                                                                const RowsDev<R> rw) {
-  if constexpr (VARIANT == 4) {
+  if constexpr (VARIANT == 6) {
+    rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, true, false, true>(c, s, out, rw, rw.table);
+  } else if constexpr (VARIANT == 4) {
     rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, false, false, true>(c, s, out, rw, rw.table);
   } else if constexpr (VARIANT == 3) {
     rows_body<R, DH, PROJ, DEG, EQUI, POW2, true, false, true>(c, s, out, rw, rw.table);

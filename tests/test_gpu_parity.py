@@ -997,3 +997,27 @@ def test_linear_and_bezier_takes_across_the_lean_index_limit():
             got = c.take_device(n_total, first, count).cpu().numpy()
             assert lib.enterp_launch_count() - before == (2 if first < lim else 1)
             assert_bits_equal(got, ref.take(n_total, first, count), f"take({n_total}) [{first}, +{count})")
+
+
+def test_take_f32_stepper_runs_with_adaptors_and_panics():
+    """Stepper runs (rows VARIANT 6): clamped / sliced f32 B-splines beyond index 2^24, incl. a slice that drives the
+    parameter out of `to_usize` range (the reference panics there): NaN for every sample of such a run, and the
+    invalid counter advances by the samples, not by the distinct values."""
+    el = rand_elements(9, 4, np.float32, 0xE5)
+    b = BSpline.builder().clamped().elements(el).equidistant("f32").degree(3).domain(0.0, 3.0).dynamic()
+    base, rbase = b.build(), oracle.OracleCurve(b.to_desc())
+    cases = [(base.clamp(), rbase.clamp()), (base.slice(0.5, 2.5), rbase.slice(0.5, 2.5)),
+             (base.clamp().slice(-1.0, 4.0), rbase.clamp().slice(-1.0, 4.0)),
+             (base.slice(0.0, 3.0e25), rbase.slice(0.0, 3.0e25))]  # scaled >= 2^64 from some index on: panics upstream
+    n32 = 1 << 32
+    windows = [(n32, (1 << 24) - 5000, 30001), (n32, (1 << 31) - 777, 5000), (n32, n32 - 40000, 40000), (n32, 3 << 29, 1 << 20)]
+    lib = _abi.load_library()
+    for c, r in cases:
+        for n_total, first, count in windows:
+            before = c.invalid_count()
+            launches = lib.enterp_launch_count()
+            got = c.take_device(n_total, first, count).cpu().numpy()
+            assert lib.enterp_launch_count() - launches in (1, 2)
+            want, inv = r.take(n_total, first, count, return_invalid=True, threads=4)
+            assert_bits_equal(got, want, f"adaptor take({n_total}) [{first}, +{count})")
+            assert c.invalid_count() - before == inv
