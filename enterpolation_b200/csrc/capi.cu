@@ -651,6 +651,65 @@ SampleSrc<R> batch_src(const void* t, uint64_t n) {
 }
 
 template <class R>
+enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const SampleSrc<R>& s, void* out, cudaStream_t st);
+
+// Ablation switch (env ENTERP_NO_GENERIC_RUNS=1): f32 takes beyond 2^26 through the generic kernels sample by sample.
+static const bool g_no_generic_runs = [] {
+  const char* v = std::getenv("ENTERP_NO_GENERIC_RUNS");
+  return v && v[0] == '1';
+}();
+constexpr uint64_t GENERIC_RUNS_FROM = 1ull << 24;   // where the runs begin (2 samples each up to 2^25)
+constexpr uint64_t GENERIC_RUNS_VALUES = 1ull << 22;  // distinct values per pass: <= 80 MB of scratch, L2-resident values
+
+// Stepper runs for every take the span-row kernels do not serve (Linear / Bezier outside the lean kernels, B-splines
+// of degree > ROWS_MAX_DEGREE or with runtime degree, ConstEquidistant knots, ...): beyond index 2^24 an f32 stepper
+// repeats its parameter in runs (rows.cuh RUNS), so per binade and per pass of <= 2^22 values the
+// distinct stepper values are generated (stepper_strided_kernel), evaluated ONCE by whatever batch kernel the curve
+// has, and expanded into the output at the store roof (runs_expand_kernel). Scratch comes from the stream-ordered
+// allocator (cudaMallocAsync on the caller's stream). Only for curves without input adaptors over a finite domain: no
+// parameter can make the reference panic, so the invalid counter needs no per-sample accounting.
+enterp_status generic_runs_take(const enterp_curve& cv, const Replica& rp, const SampleSrc<float>& s, void* out, cudaStream_t st) {
+  const Resolved& r = cv.core->r;
+  const size_t stride = sizeof(float) * (size_t)r.dim;
+  const uint64_t A = s.first, B = s.first + s.count;
+  uint64_t pos = A;
+  if (pos < GENERIC_RUNS_FROM) {  // the head keeps the per-sample kernels
+    SampleSrc<float> head = s;
+    head.count = GENERIC_RUNS_FROM - A;
+    const enterp_status es = dispatch_eval<float>(cv, rp, head, out, st);
+    if (es) return es;
+    pos = GENERIC_RUNS_FROM;
+  }
+  while (pos < B) {
+    const int hb = 63 - __builtin_clzll(pos);
+    const unsigned ls = (unsigned)(hb - 23);
+    const uint64_t binade_end = hb >= 63 ? B : (1ull << (hb + 1));
+    uint64_t end = B < binade_end ? B : binade_end;
+    if (end - pos > (GENERIC_RUNS_VALUES << ls)) end = pos + (GENERIC_RUNS_VALUES << ls);
+    const uint64_t vb = (pos >> ls) << ls;
+    const uint64_t nvals = ((end - 1 - vb) >> ls) + 2;
+    void* scratch = nullptr;
+    const size_t t_bytes = (nvals * sizeof(float) + 255) / 256 * 256;
+    CK(cudaMallocAsync(&scratch, t_bytes + nvals * stride, st), "cudaMallocAsync");
+    float* t = static_cast<float*>(scratch);
+    void* vals = static_cast<char*>(scratch) + t_bytes;
+    SampleSrc<float> ts = s;  // same step / start, indices in units of 2^ls
+    ts.first = vb >> ls;
+    ts.count = nvals;
+    cudaError_t e = launch_stepper_strided<float>(ts, ls, t, st);
+    enterp_status es = e == cudaSuccess ? dispatch_eval<float>(cv, rp, batch_src<float>(t, nvals), vals, st) : cuda_fail(e, "stepper launch");
+    if (es == ENTERP_OK) {
+      e = launch_runs_expand((int)r.dim, vals, static_cast<char*>(out) + (pos - A) * stride, pos, end - pos, vb, ls, st);
+      if (e != cudaSuccess) es = cuda_fail(e, "runs expand launch");
+    }
+    cudaFreeAsync(scratch, st);
+    if (es) return es;
+    pos = end;
+  }
+  return ENTERP_OK;
+}
+
+template <class R>
 enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const SampleSrc<R>& s, void* out, cudaStream_t st) {
   const Resolved& r = cv.core->r;
   // The lean Linear / Bezier take kernels index with 32 bits and stop at 2^32 - 2^24 (inst_lean.cuh): a take that
@@ -669,6 +728,14 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
   const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 16u) == 0;
   const bool proj = r.weighted != 0;
   const bool equi = r.knot_base != ENTERP_KNOTS_SORTED;
+  // a take the generic kernels would evaluate sample by sample although its f32 stepper repeats itself (see above)
+  const bool generic_runs = sizeof(R) == 4 && s.t == nullptr && !g_no_generic_runs && cv.pre.empty() && vec_ok &&
+                            std::isfinite(r.domain[0]) && std::isfinite(r.domain[1]) && s.first + s.count >= GENERIC_RUNS_FROM + (1ull << 16) &&
+                            s.first + s.count < (1ull << 62);
+  auto take_runs = [&]() -> enterp_status {
+    if constexpr (sizeof(R) == 4) return generic_runs_take(cv, rp, s, out, st);
+    return ENTERP_UNSUPPORTED;
+  };
   cudaError_t e;
   switch (r.kind) {
     case ENTERP_BSPLINE: {
@@ -690,15 +757,19 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
         rw.ri_off = (uint32_t)((int64_t)r.map_add - (int64_t)r.rows_lo);
         rw.pow2_ops = r.rows_pow2_ops;
         e = launch_bspline_rows<R>(r.dh, proj, deg, equi, r.rows_mode == 1, d, s, static_cast<R*>(out), rw, st);
-        if (e == cudaErrorNotSupported)  // table too big for shared memory and not a plain take(): generic kernel
+        if (e == cudaErrorNotSupported) {  // table too big for shared memory and not a plain take(): generic kernel
+          if (generic_runs) return take_runs();
           e = launch_bspline<R>(r.dh, proj, deg, equi, d, s, static_cast<R*>(out), vec_ok, st);
+        }
       } else {
+        if (generic_runs) return take_runs();
         e = launch_bspline<R>(r.dh, proj, deg, equi, d, s, static_cast<R*>(out), vec_ok, st);
       }
       break;
     }
     case ENTERP_LINEAR:
       if (!g_disable_lean && !g_ballot_search && lean_linear<R>(r.dh, proj, equi, d, s, static_cast<R*>(out), vec_ok, st, &e)) break;
+      if (generic_runs) return take_runs();
       e = launch_linear<R>(r.dh, proj, equi, d, s, static_cast<R*>(out), vec_ok, st);
       break;
     default: {
@@ -707,6 +778,7 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
       if (!g_disable_lean && lean_bezier<R>(r.dh, proj, n, reinterpret_cast<const R*>(r.elems.data()), d, s,
                                                  static_cast<R*>(out), vec_ok, st, &e))
         break;
+      if (generic_runs) return take_runs();
       e = launch_bezier<R>(r.dh, proj, n, d, s, static_cast<R*>(out), vec_ok, st);
       break;
     }

@@ -153,4 +153,17 @@ static cudaError_t launch_deriv_impl(int dim, const CurveDev<R>& c, const Sample
 ENTERP_SPECIALIZE(float)
 ENTERP_SPECIALIZE(double)
 
+cudaError_t launch_runs_expand(int words, const void* vals, void* out, unsigned long long a, unsigned long long count,
+                               unsigned long long vb, unsigned ls, cudaStream_t st) {
+  const uint32_t* v = static_cast<const uint32_t*>(vals);
+  uint32_t* o = static_cast<uint32_t*>(out);
+  switch (words) {
+    case 1: return launch_grid_stride(runs_expand_kernel<1>, count, BLOCK * 4, st, v, o, a, count, vb, ls);
+    case 2: return launch_grid_stride(runs_expand_kernel<2>, count, BLOCK * 4, st, v, o, a, count, vb, ls);
+    case 3: return launch_grid_stride(runs_expand_kernel<3>, count, BLOCK * 4, st, v, o, a, count, vb, ls);
+    case 4: return launch_grid_stride(runs_expand_kernel<4>, count, BLOCK * 4, st, v, o, a, count, vb, ls);
+  }
+  return cudaErrorInvalidValue;
+}
+
 }  // namespace enterp

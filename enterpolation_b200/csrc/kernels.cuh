@@ -1159,6 +1159,30 @@ __global__ void __launch_bounds__(BLOCK) stepper_strided_kernel(const SampleSrc<
     out[j] = xadd(xmul(s.step, from_index((s.first + j) << ls, R(0))), s.start);
 }
 
+// Generic stepper runs (capi.cu generic_runs_take): out[i] = vals[m(a + i)] for i in [0, count), m = the index of the
+// distinct value sample a + i reads: RN-even((a + i - vb) / 2^ls), the integer form of from_usize's rounding (rows.cuh
+// RUNS). W = 32-bit words per element. The 32 lanes of a warp read one or two values (L1 broadcasts) and store
+// coalesced: the kernel runs at the store roof whatever produced `vals`.
+template <int W>
+__global__ void __launch_bounds__(BLOCK) runs_expand_kernel(const uint32_t* __restrict__ vals, uint32_t* __restrict__ out,
+                                                            unsigned long long a, unsigned long long count,
+                                                            unsigned long long vb, unsigned ls) {
+  const unsigned long long hm1 = ((1ull << ls) >> 1) - 1ull, vq = (vb >> ls) & 1ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; i < count;
+       i += (unsigned long long)gridDim.x * BLOCK) {
+    const unsigned long long dd = a + i - vb;
+    const unsigned long long m = (dd + hm1 + (((dd >> ls) + vq) & 1ull)) >> ls;
+    if constexpr (W == 4) {
+      __stcs(reinterpret_cast<float4*>(out) + i, __ldg(reinterpret_cast<const float4*>(vals) + m));
+    } else if constexpr (W == 2) {
+      __stcs(reinterpret_cast<float2*>(out) + i, __ldg(reinterpret_cast<const float2*>(vals) + m));
+    } else {
+#pragma unroll
+      for (int q = 0; q < W; ++q) __stcs(out + i * W + q, __ldg(vals + m * W + q));
+    }
+  }
+}
+
 template <class R>
 __global__ void __launch_bounds__(BLOCK) stepper_kernel(const SampleSrc<R> s, R* __restrict__ out) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; i < s.count;

@@ -98,4 +98,8 @@ cudaError_t launch_stepper(const SampleSrc<R>& s, R* out, cudaStream_t st);
 template <class R>
 cudaError_t launch_stepper_strided(const SampleSrc<R>& s, unsigned ls, R* out, cudaStream_t st);
 
+// out[i] = vals[m(a + i)] (kernels.cuh runs_expand_kernel); words = 32-bit words per element (1..4)
+cudaError_t launch_runs_expand(int words, const void* vals, void* out, unsigned long long a, unsigned long long count,
+                               unsigned long long vb, unsigned ls, cudaStream_t st);
+
 }  // namespace enterp
