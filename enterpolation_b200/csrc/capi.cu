@@ -668,8 +668,31 @@ constexpr uint64_t GENERIC_RUNS_VALUES = 1ull << 22;  // distinct values per pas
 // has, and expanded into the output at the store roof (runs_expand_kernel). Scratch comes from the stream-ordered
 // allocator (cudaMallocAsync on the caller's stream). Only for curves without input adaptors over a finite domain: no
 // parameter can make the reference panic, so the invalid counter needs no per-sample accounting.
+// The device's default stream-ordered pool returns freed memory to the OS at the next synchronisation unless told to
+// keep some: let it keep the scratch of one pass, so that repeated takes do not re-allocate it every call.
+static void keep_scratch_in_pool(int device) {
+  static std::mutex mu;
+  static std::vector<char> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)done.size() <= device) done.resize(device + 1, 0);
+  if (done[device]) return;
+  done[device] = 1;
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+    uint64_t keep = 0;
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    const uint64_t want = 128ull << 20;
+    if (keep < want) {
+      keep = want;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  cudaGetLastError();
+}
+
 enterp_status generic_runs_take(const enterp_curve& cv, const Replica& rp, const SampleSrc<float>& s, void* out, cudaStream_t st) {
   const Resolved& r = cv.core->r;
+  keep_scratch_in_pool(rp.device);
   const size_t stride = sizeof(float) * (size_t)r.dim;
   const uint64_t A = s.first, B = s.first + s.count;
   uint64_t pos = A;
