@@ -29,24 +29,26 @@ pub use enterpolation_b200_sys as sys;
 pub trait Scalar: num_traits::real::Real + num_traits::FromPrimitive + Copy + 'static {
     /// `ENTERP_F32` / `ENTERP_F64`.
     const CODE: i32;
-    fn from_f64(v: f64) -> Self;
-    fn to_f64(self) -> f64;
+    /// The ABI carries scalar constants as `f64`: exact for `f64`, the nearest `f32` for `f32` (the values it carries
+    /// back were widened from `f32` by the library, so nothing is lost). Named apart from num-traits' `from_f64`/`to_f64`.
+    fn narrow(v: f64) -> Self;
+    fn widen(self) -> f64;
 }
 impl Scalar for f32 {
     const CODE: i32 = sys::ENTERP_F32;
-    fn from_f64(v: f64) -> Self {
+    fn narrow(v: f64) -> Self {
         v as f32
     }
-    fn to_f64(self) -> f64 {
+    fn widen(self) -> f64 {
         self as f64
     }
 }
 impl Scalar for f64 {
     const CODE: i32 = sys::ENTERP_F64;
-    fn from_f64(v: f64) -> Self {
+    fn narrow(v: f64) -> Self {
         v
     }
-    fn to_f64(self) -> f64 {
+    fn widen(self) -> f64 {
         self
     }
 }
@@ -272,12 +274,12 @@ impl<R: Scalar, T: Element<R>> Description<R, T> {
     pub fn domain(mut self, start: R, end: R) -> Self {
         if self.d.kind == sys::ENTERP_BEZIER {
             self.d.input_form = sys::ENTERP_INPUT_DOMAIN;
-            self.d.in_a = start.to_f64();
-            self.d.in_b = end.to_f64();
+            self.d.in_a = start.widen();
+            self.d.in_b = end.widen();
         } else {
             self.d.eq_form = sys::ENTERP_EQ_DOMAIN;
-            self.d.eq_a = start.to_f64();
-            self.d.eq_b = end.to_f64();
+            self.d.eq_a = start.widen();
+            self.d.eq_b = end.widen();
         }
         self
     }
@@ -293,8 +295,8 @@ impl<R: Scalar, T: Element<R>> Description<R, T> {
     /// `.distance(start, step)`
     pub fn distance(mut self, start: R, step: R) -> Self {
         self.d.eq_form = sys::ENTERP_EQ_DISTANCE;
-        self.d.eq_a = start.to_f64();
-        self.d.eq_b = step.to_f64();
+        self.d.eq_a = start.widen();
+        self.d.eq_b = step.widen();
         self
     }
     /// `.constant::<N>()`
@@ -465,8 +467,8 @@ impl<R: Scalar, T: Element<R>> DeviceCurve<R, T> {
         let mut h: *mut sys::enterp_curve = core::ptr::null_mut();
         // SAFETY: valid handle
         let st = unsafe {
-            sys::enterp_curve_slice(self.h, start.is_some() as i32, start.map_or(0.0, Scalar::to_f64), end.is_some() as i32,
-                                    end.map_or(0.0, Scalar::to_f64), &mut h)
+            sys::enterp_curve_slice(self.h, start.is_some() as i32, start.map_or(0.0, Scalar::widen), end.is_some() as i32,
+                                    end.map_or(0.0, Scalar::widen), &mut h)
         };
         check(st, &no_info())?;
         Ok(DeviceCurve { h, device: self.device, _r: PhantomData })
@@ -495,7 +497,7 @@ impl<R: Scalar, T: Element<R>> Curve<R> for DeviceCurve<R, T> {
         let mut d = [0f64; 2];
         // SAFETY: valid handle, `d` has room for two doubles; the call cannot fail for a built curve
         unsafe { sys::enterp_curve_domain(self.h, d.as_mut_ptr()) };
-        [R::from_f64(d[0]), R::from_f64(d[1])]
+        [R::narrow(d[0]), R::narrow(d[1])]
     }
 }
 
