@@ -166,6 +166,10 @@ struct HostPipe {
   HostBuf rle_stage[2];        // ... and the pinned landing buffers of the distinct values
   cudaStream_t rstream[2] = {nullptr, nullptr};
   cudaEvent_t rdone[2] = {nullptr, nullptr};
+  // what this pipe has learnt about its host (kept across calls): the plain pipeline's rate, and how often in a row the
+  // hybrid pipeline failed to beat it (hosts whose memory system is busy elsewhere)
+  double plain_gbs = 0;
+  int hybrid_bad = 0;
   cudaStream_t stream[2] = {nullptr, nullptr};
   cudaEvent_t done[2] = {nullptr, nullptr};
   bool busy = false;
@@ -894,6 +898,13 @@ struct HostLane {
   HostPipe* hp = nullptr;
   uint64_t off0 = 0, count = 0, chunk = 0, next = 0, k = 0, kr = 0;
   enterp_status err = ENTERP_OK;  // first failure of a chunk issued from inside a host fill (j.feed)
+  // Adaptive choice between the hybrid and the plain pipeline: claims are paced by completions (the slots are few), so
+  // the bytes claimed per window of HOST_WINDOW chunks over the wall-clock time of the window is the current rate.
+  std::chrono::steady_clock::time_point win_t0;
+  uint64_t win_bytes = 0;
+  int win_n = 0;
+  bool plain_mode = false;  // eligible chunks take the plain pipeline for now
+  int plain_windows = 0;    // ... for this many more windows
   struct Pending {
     bool live = false;
     uint64_t off = 0, n = 0;
@@ -1041,6 +1052,42 @@ enterp_status rle_issue(const HostJob& j, HostLane& l, int b, uint64_t off, uint
   return ENTERP_OK;
 }
 
+constexpr int HOST_WINDOW = 8;
+
+// Called for every claimed chunk of a run-length capable call. Hosts differ (and change) a lot in what their cores can
+// add to the copy engine's rate — from 3x down to less than nothing when the memory system is busy elsewhere — so the
+// lane measures: a plain window gives the reference rate (remembered per pipe), a hybrid window that does not beat it
+// sends the next four windows down the plain pipeline before the hybrid one is tried again.
+void lane_account(const HostJob& j, HostLane& l, uint64_t n) {
+  if (!j.hybrid) return;
+  const auto now = std::chrono::steady_clock::now();
+  if (l.win_n == 0) l.win_t0 = now;
+  if (l.win_n < HOST_WINDOW) {
+    l.win_bytes += n * j.out_stride;
+    ++l.win_n;
+    return;
+  }
+  const double secs = std::chrono::duration<double>(now - l.win_t0).count();
+  const double gbs = secs > 0 ? (double)l.win_bytes / secs / 1e9 : 0;
+  HostPipe& hp = *l.hp;
+  if (l.plain_mode) {
+    hp.plain_gbs = gbs;
+    if (--l.plain_windows <= 0) l.plain_mode = false;
+  } else if (hp.plain_gbs <= 0) {
+    l.plain_mode = true;  // no reference yet on this pipe: one plain window
+    l.plain_windows = 1;
+  } else if (gbs < 1.02 * hp.plain_gbs) {
+    l.plain_mode = true;
+    l.plain_windows = 4;
+    if (hp.hybrid_bad < 3) ++hp.hybrid_bad;
+  } else {
+    hp.hybrid_bad = 0;
+  }
+  l.win_t0 = now;
+  l.win_bytes = n * j.out_stride;
+  l.win_n = 1;
+}
+
 // Hands the lane's next chunk to the copy engine if one of its plain slots is free (non-blocking).
 enterp_status feed_lane(const HostJob& j, HostLane& l) {
   if (!l.hp || l.next >= l.count) return ENTERP_OK;
@@ -1055,6 +1102,7 @@ enterp_status feed_lane(const HostJob& j, HostLane& l) {
       const enterp_status es = plain_issue(j, l, b, off, n);
       if (es) return es;
       l.next = off + n;
+      lane_account(j, l, n);
       return ENTERP_OK;
     }
   }
@@ -1068,15 +1116,21 @@ enterp_status lane_step(const HostJob& j, HostLane& l) {
   const uint64_t off = l.next;
   const uint64_t n = l.count - off < l.chunk ? l.count - off : l.chunk;
   unsigned ls = 0;
-  const bool eligible = rle_eligible(j, j.first + l.off0 + off, n, &ls);
+  const bool eligible = !l.plain_mode && rle_eligible(j, j.first + l.off0 + off, n, &ls);
   bool done = true;
   if (!eligible) {  // the classic double-buffered pipeline: wait for the slot used two chunks ago
+    if (l.plain_mode) {  // leaving the hybrid pipeline: its pending fills first, so that they do not trail the call
+      for (int b = 0; b < 2; ++b) CK(rle_finish(j, l, (int)((l.kr + b) & 1)), "run-length wait");
+      if (l.err) return l.err;
+      if (l.next != off) return ENTERP_OK;  // the fills' feed claimed chunks meanwhile: look again
+    }
     const int b = (int)(l.k & 1);
     CK(plain_finish(j, l, b, true, &done), "pipeline wait");
     const enterp_status es = plain_issue(j, l, b, off, n);
     if (es) return es;
     ++l.k;
     l.next = off + n;
+    lane_account(j, l, n);
     return ENTERP_OK;
   }
   if (j.hybrid) {  // a free plain slot means an idle copy engine: feed it first
@@ -1098,6 +1152,7 @@ enterp_status lane_step(const HostJob& j, HostLane& l) {
   if (es) return es;
   ++l.kr;
   l.next = off2 + n2;
+  lane_account(j, l, n2);
   return ENTERP_OK;
 }
 
@@ -1155,6 +1210,10 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
     l.hp = acquire_pipe(l.device);
     const cudaError_t e = lane_prepare(j, l);
     if (e != cudaSuccess) st = cuda_fail(e, "host pipeline scratch");
+    if (j.hybrid && l.hp->hybrid_bad >= 2) {  // this host did not profit from the fills lately: start plain, probe later
+      l.plain_mode = true;
+      l.plain_windows = 4;
+    }
   }
   if (j.hybrid)
     j.feed = [&j, &lanes]() {
