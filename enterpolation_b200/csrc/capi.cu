@@ -1053,6 +1053,11 @@ enterp_status rle_issue(const HostJob& j, HostLane& l, int b, uint64_t off, uint
 }
 
 constexpr int HOST_WINDOW = 8;
+// Debug switch (env ENTERP_HOST_TRACE=1): one stderr line per window of the host pipeline.
+static const bool g_host_trace = [] {
+  const char* v = std::getenv("ENTERP_HOST_TRACE");
+  return v && v[0] == '1';
+}();
 
 // Called for every claimed chunk of a run-length capable call. Hosts differ (and change) a lot in what their cores can
 // add to the copy engine's rate — from 3x down to less than nothing when the memory system is busy elsewhere — so the
@@ -1070,6 +1075,9 @@ void lane_account(const HostJob& j, HostLane& l, uint64_t n) {
   const double secs = std::chrono::duration<double>(now - l.win_t0).count();
   const double gbs = secs > 0 ? (double)l.win_bytes / secs / 1e9 : 0;
   HostPipe& hp = *l.hp;
+  if (g_host_trace)
+    std::fprintf(stderr, "[enterp host] dev %d window %s %.1f GB/s (plain reference %.1f, hybrid_bad %d)\n", l.device,
+                 l.plain_mode ? "plain " : "hybrid", gbs, hp.plain_gbs, hp.hybrid_bad);
   if (l.plain_mode) {
     hp.plain_gbs = gbs;
     if (--l.plain_windows <= 0) l.plain_mode = false;
