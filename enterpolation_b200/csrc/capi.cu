@@ -156,12 +156,16 @@ struct DeviceGuard {
 // device no longer serialise on a single mutex; idle pipes are freed by enterp_host_scratch_release().
 // Every buffer carries its OWN size, reset to 0 whenever the buffer is freed, so a failed (re)allocation can
 // never leave a null pointer behind a non-zero recorded size.
+// Plain pipeline depth: chunks the copy engine has queued ahead. Two suffice on a quiet host; four ride out the
+// scheduling hiccups of a shared one (a host thread that is late by a few milliseconds no longer starves the DMA).
+constexpr int PLAIN_SLOTS = 4;
+
 struct HostBuf {
   void* p = nullptr;
   size_t bytes = 0;
 };
 struct HostPipe {
-  HostBuf dev_in[2], dev_out[2], stage_in[2], stage_out[2];
+  HostBuf dev_in[PLAIN_SLOTS], dev_out[PLAIN_SLOTS], stage_in[PLAIN_SLOTS], stage_out[PLAIN_SLOTS];
   HostBuf rle_t[2], rle_v[2];  // run-length pipeline: stepper values and their evaluations on the device
   HostBuf rle_stage[2];        // ... and the pinned landing buffers of the distinct values
   cudaStream_t rstream[2] = {nullptr, nullptr};
@@ -170,8 +174,8 @@ struct HostPipe {
   // hybrid pipeline failed to beat it (hosts whose memory system is busy elsewhere)
   double plain_gbs = 0;
   int hybrid_bad = 0;
-  cudaStream_t stream[2] = {nullptr, nullptr};
-  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaStream_t stream[PLAIN_SLOTS] = {};
+  cudaEvent_t done[PLAIN_SLOTS] = {};
   bool busy = false;
 };
 
@@ -243,18 +247,20 @@ static int release_idle_pipes(int device) {
         ++i;
         continue;
       }
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < PLAIN_SLOTS; ++b) {
         free_buf(hp->dev_in[b], false);
         free_buf(hp->dev_out[b], false);
         free_buf(hp->stage_in[b], true);
         free_buf(hp->stage_out[b], true);
+        if (hp->stream[b]) cudaStreamDestroy(hp->stream[b]);
+        if (hp->done[b]) cudaEventDestroy(hp->done[b]);
+      }
+      for (int b = 0; b < 2; ++b) {
         free_buf(hp->rle_stage[b], true);
         free_buf(hp->rle_t[b], false);
         free_buf(hp->rle_v[b], false);
         if (hp->rstream[b]) cudaStreamDestroy(hp->rstream[b]);
         if (hp->rdone[b]) cudaEventDestroy(hp->rdone[b]);
-        if (hp->stream[b]) cudaStreamDestroy(hp->stream[b]);
-        if (hp->done[b]) cudaEventDestroy(hp->done[b]);
       }
       delete hp;
       v.erase(v.begin() + i);
@@ -910,7 +916,7 @@ struct HostLane {
     uint64_t off = 0, n = 0;
     uint64_t vb = 0;      // run-length chunks: representable index at or below the chunk's first sample
     unsigned ls = 0;      // log2 of the run length (fl() spacing of the chunk's binade)
-  } pend[2], rpend[2];
+  } pend[PLAIN_SLOTS], rpend[2];
 };
 
 struct HostJob {
@@ -931,15 +937,17 @@ constexpr unsigned RLE_MIN_SHIFT = 2;  // runs of at least 4 samples (indices fr
 cudaError_t lane_prepare(const HostJob& j, HostLane& l) {
   HostPipe& hp = *l.hp;
   cudaError_t e;
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < PLAIN_SLOTS; ++b) {
     if (!hp.stream[b] && (e = cudaStreamCreateWithFlags(&hp.stream[b], cudaStreamNonBlocking)) != cudaSuccess) return e;
     if (!hp.done[b] && (e = cudaEventCreateWithFlags(&hp.done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
     if (!j.take && (e = ensure(hp.dev_in[b], l.chunk * j.rs, false)) != cudaSuccess) return e;
     if ((e = ensure(hp.dev_out[b], l.chunk * j.out_stride, false)) != cudaSuccess) return e;
     if (!j.take && !j.pin_in && (e = ensure(hp.stage_in[b], l.chunk * j.rs, true)) != cudaSuccess) return e;
     if (!j.pin_out && (e = ensure(hp.stage_out[b], l.chunk * j.out_stride, true)) != cudaSuccess) return e;
-    if (j.rle) {
-      const size_t max_vals = (size_t)(l.chunk >> RLE_MIN_SHIFT) + 2;
+  }
+  if (j.rle) {
+    const size_t max_vals = (size_t)(l.chunk >> RLE_MIN_SHIFT) + 2;
+    for (int b = 0; b < 2; ++b) {
       if (!hp.rstream[b] && (e = cudaStreamCreateWithFlags(&hp.rstream[b], cudaStreamNonBlocking)) != cudaSuccess) return e;
       if (!hp.rdone[b] && (e = cudaEventCreateWithFlags(&hp.rdone[b], cudaEventDisableTiming)) != cudaSuccess) return e;
       if ((e = ensure(hp.rle_t[b], max_vals * j.rs, false)) != cudaSuccess) return e;
@@ -1101,7 +1109,7 @@ enterp_status feed_lane(const HostJob& j, HostLane& l) {
   if (!l.hp || l.next >= l.count) return ENTERP_OK;
   DeviceGuard g(l.device);
   if (!g.ok) return ENTERP_NO_DEVICE;
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < PLAIN_SLOTS; ++b) {
     bool done = true;
     CK(plain_finish(j, l, b, false, &done), "pipeline poll");
     if (done) {
@@ -1132,7 +1140,7 @@ enterp_status lane_step(const HostJob& j, HostLane& l) {
       if (l.err) return l.err;
       if (l.next != off) return ENTERP_OK;  // the fills' feed claimed chunks meanwhile: look again
     }
-    const int b = (int)(l.k & 1);
+    const int b = (int)(l.k % PLAIN_SLOTS);
     CK(plain_finish(j, l, b, true, &done), "pipeline wait");
     const enterp_status es = plain_issue(j, l, b, off, n);
     if (es) return es;
@@ -1251,17 +1259,17 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
         if (e != cudaSuccess) st = cuda_fail(e, "run-length drain");
         if (st == ENTERP_OK) st = l.err;
       }
-      for (int b = 0; b < 2 && st == ENTERP_OK; ++b) {
+      for (int b = 0; b < PLAIN_SLOTS && st == ENTERP_OK; ++b) {
         bool done = true;
         const cudaError_t e = plain_finish(j, l, b, true, &done);
         if (e != cudaSuccess) st = cuda_fail(e, "pipeline drain");
       }
     }
     if (st != ENTERP_OK) {
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < PLAIN_SLOTS; ++b)
         if (l.hp->stream[b]) cudaStreamSynchronize(l.hp->stream[b]);
+      for (int b = 0; b < 2; ++b)
         if (l.hp->rstream[b]) cudaStreamSynchronize(l.hp->rstream[b]);
-      }
     }
     release_pipe(l.hp);
   }
