@@ -1070,7 +1070,7 @@ static const bool g_host_trace = [] {
 // Called for every claimed chunk of a run-length capable call. Hosts differ (and change) a lot in what their cores can
 // add to the copy engine's rate — from 3x down to less than nothing when the memory system is busy elsewhere — so the
 // lane measures: a plain window gives the reference rate (remembered per pipe), a hybrid window that does not beat it
-// sends the next four windows down the plain pipeline before the hybrid one is tried again.
+// sends the next 4 (then 8, 16, 32) windows down the plain pipeline before the hybrid one is tried again.
 void lane_account(const HostJob& j, HostLane& l, uint64_t n) {
   if (!j.hybrid) return;
   const auto now = std::chrono::steady_clock::now();
@@ -1094,7 +1094,7 @@ void lane_account(const HostJob& j, HostLane& l, uint64_t n) {
     l.plain_windows = 1;
   } else if (gbs < 1.02 * hp.plain_gbs) {
     l.plain_mode = true;
-    l.plain_windows = 4;
+    l.plain_windows = 4 << hp.hybrid_bad;  // 4, 8, 16, 32 windows: the longer the fills have not paid, the rarer the probes
     if (hp.hybrid_bad < 3) ++hp.hybrid_bad;
   } else {
     hp.hybrid_bad = 0;
