@@ -736,7 +736,9 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
       const R first = inner[0], last = inner[s.inner_len - 1];
       // Two cells per knot: ~75 % of the samples are served by their first gather, ~22 % by the second, ~3 % walk the
       // index (C2, G samples/s: no slots 99.9, 1 cell per knot 102.5, 2: 127.2, 4: 81.6 — a 128 MB table no longer
-      // shares the L2). The table is 2 x the records; beyond 64 MiB it is not built (the index + records path stays).
+      // shares the L2; cells as a percentage of the knots, ENTERP_SLOTS_CELLS_PERCENT: 125 % 111.4, 150 % 122.1, 175 % 129.6,
+      // 200 % 128.9, 250 % 117.3, 300 % 100.7). The table is 2 x the records; beyond 64 MiB it is not built (the index +
+      // records path stays).
       uint64_t per_knot = 2;
       if (const char* e = std::getenv("ENTERP_SLOTS_PER_KNOT")) {  // ablation: 0 (off), 1, 2, 4
         const long v = std::atol(e);
@@ -746,7 +748,11 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
           !r.buckets.empty()) {
         uint64_t ns = 1;
         while (ns < per_knot * s.inner_len) ns <<= 1;
-        const bool ablation = std::getenv("ENTERP_SLOTS_PER_KNOT") != nullptr;
+        if (const char* e = std::getenv("ENTERP_SLOTS_CELLS_PERCENT")) {  // ablation: cells as a percentage of the knots (any count works)
+          const long v = std::atol(e);
+          if (v >= 50 && v <= 800) ns = (uint64_t)((double)s.inner_len * (double)v / 100.0);
+        }
+        const bool ablation = std::getenv("ENTERP_SLOTS_PER_KNOT") != nullptr || std::getenv("ENTERP_SLOTS_CELLS_PERCENT") != nullptr;
         if (!ablation && (ns + 1) * stride * sizeof(R) > (64ull << 20) + stride * sizeof(R)) ns = 0;
         while (ns > 1 && (ns + 1) * stride * sizeof(R) > (1ull << 28)) ns >>= 1;
         const R inv = (R)ns / (last - first);
