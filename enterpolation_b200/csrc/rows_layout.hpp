@@ -9,7 +9,7 @@
 namespace enterp {
 
 // Highest degree with span-row kernels. The default build instantiates degrees 1..4 (what the reference's examples,
-// benches and BASELINE.json's configs use): an 18 MB library. `make ROWS_MAX_DEGREE=7` adds 5..7: 35 MB, 2:45 instead of
+// benches and BASELINE.json's configs use): a 20 MB library. `make ROWS_MAX_DEGREE=7` adds 5..7: 35 MB, 2:45 instead of
 // 1:30 min of nvcc on 8 cores, and take(2^26) of a degree-5 / degree-7 `[f32;4]` curve at 60 / 61 instead of 51 / 36 G
 // samples/s (f64 scalar: 84 / 41 instead of 45 / 30). Above the limit B-splines run through the generic kernel
 // (compile-time degree up to 7).
