@@ -173,5 +173,20 @@ kat(name="adaptors_slice_test", src="src/base/adaptors.rs:359-368",
     sample=[0.0, 1.0], expect=[10.0, 100.0], ulps=4)
 
 
+# adaptors.rs:338-356 wraps the Identity curve in TransformInput::new(identity, 0.0, 2.0); over [0,1] (and beyond: both
+# extrapolate linearly) Identity is the two-point Bezier 0 -> 1, and a stored TransformInput is what the serde layout
+# hands to the library verbatim (ENTERP_INPUT_TRANSFORM). The take() half pins TransformInput::domain (adaptors.rs:158-167)
+def _identity_times_two():
+    from enterpolation_b200 import serde
+    return serde.loads("bezier", '{"addition":0.0,"multiplication":2.0,"inner":'
+                       '{"elements":[0.0,1.0],"space":{"_phantom":null},"_input":null}}', "f64")
+
+
+kat(name="adaptors_input_transform_extract", src="src/base/adaptors.rs:338-347", make=_identity_times_two,
+    sample=[1.0, 0.0, 0.5, 1.0], expect=[2.0, 0.0, 1.0, 2.0], ulps=4)
+kat(name="adaptors_input_transform_take", src="src/base/adaptors.rs:348-355", make=_identity_times_two,
+    take=3, expect=[0.0, 0.5, 1.0], ulps=4)
+
+
 def all_kats():
     return KATS
