@@ -1,6 +1,8 @@
 """Seeded random differential test: random curve configurations x random evaluation calls, CUDA path vs CPU oracle,
 bit for bit. Complements the structured cases of test_gpu_parity.py by mixing features the kernels dispatch on
 (table sizes around the shared-memory / bucket-index / lean-kernel thresholds, adaptors, easings, weights, windows)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -109,7 +111,12 @@ def _check(rng, scalar, b, tag):
         assert c.invalid_count() - before == inv, f"{tag} {what} batch invalid count"
 
 
-@pytest.mark.parametrize("seed", range(24))
+# ENTERP_FUZZ_SEEDS="first:count" widens the sweep (e.g. "24:400" on a spare GPU minute); the default 24 seeds x 12
+# curves are what every `pytest -m gpu` run covers.
+_FIRST, _COUNT = (int(v) for v in os.environ.get("ENTERP_FUZZ_SEEDS", "0:24").split(":"))
+
+
+@pytest.mark.parametrize("seed", range(_FIRST, _FIRST + _COUNT))
 def test_random_curves(seed):
     rng = np.random.default_rng(0xE17E + seed)
     done = 0
@@ -120,4 +127,62 @@ def test_random_curves(seed):
         except Exception:
             continue  # the random shape violated a builder rule (covered by test_builder_errors.py)
         _check(rng, scalar, b, f"seed {seed} case {done}")
+        done += 1
+
+
+def _random_const_equidistant(rng):
+    """ConstEquidistant knots (list.rs:566-721): no builder chain reaches them, so _random_curve never does."""
+    scalar = rng.choice(["f32", "f64"])
+    dtype = DT[scalar]
+    dim = int(rng.integers(1, 5))
+    n = int(rng.choice([2, 3, 9, 33, 200, 5000]))
+    el = (rng.random((n, dim)) * 2 - 1).astype(dtype)
+    el = el if dim > 1 else el[:, 0]
+    if rng.random() < 0.5:
+        return scalar, Linear.equidistant_unchecked(el, scalar)
+    degree = int(rng.choice([1, 2, 3, 4, 6]))
+    if n <= degree:
+        return scalar, Linear.equidistant_unchecked(el, scalar)
+    w = (0.25 + rng.random(n)).astype(dtype) if rng.random() < 0.3 else None
+    return scalar, BSpline.new_const_equidistant(el, n + degree - 1, scalar, workspace=None if rng.random() < 0.5 else degree + 1, weights=w)
+
+
+# Windows of long takes laid over the indices where an f32 stepper changes its run length (2^24 .. 2^32, rows.cuh RUNS,
+# capi.cu generic_runs_take / run-length host transfer), for random curves, through the device AND the host-buffer entry
+# points (the latter decide per chunk between the plain and the run-length pipeline).
+@pytest.mark.parametrize("seed", range(_FIRST // 2, _FIRST // 2 + max(1, _COUNT // 2)))
+def test_random_windows_over_run_boundaries(seed):
+    from enterpolation_b200.curve import Take
+    rng = np.random.default_rng(0xB0DA + seed)
+    done = 0
+    while done < 6:
+        scalar, b = _random_const_equidistant(rng) if rng.random() < 0.2 else _random_curve(rng)
+        try:
+            c = b.build()
+        except Exception:
+            continue
+        r = oracle.OracleCurve(b.to_desc())
+        variants = [(c, r, "plain")]
+        if rng.random() < 0.25:
+            variants.append((c.clamp(), r.clamp(), "clamp"))
+        for cv, rv, what in variants:
+            k = int(rng.integers(24, 33))
+            n = int(rng.choice([4099, 70001, 300000]))
+            first = (1 << k) - int(rng.integers(0, n + 1))
+            total = first + n + int(rng.choice([0, 1, 12345, 1 << k]))
+            tag = f"seed {seed} case {done} {what} take({total})[{first}:+{n}]"
+            want, inv = rv.take(total, first, n, return_invalid=True)
+            before = c.invalid_count()
+            got = cv.take_device(total, first, n).cpu().numpy()
+            assert_bits_equal(got, want, tag + " device")
+            assert c.invalid_count() - before == inv, tag + " invalid count"
+            got = Take(cv, total, first, n).collect()
+            assert_bits_equal(got, want, tag + " host")
+            m = int(rng.choice([1, 1000, 20011]))
+            d = rv.domain()
+            lo, hi = float(d[0]), float(d[1])
+            span = hi - lo if np.isfinite(hi - lo) and hi > lo else 1.0
+            t = (rng.random(m) * 1.6 * span + (lo - 0.3 * span)).astype(DT[scalar])
+            want, inv = rv.eval(t, return_invalid=True)
+            assert_bits_equal(np.asarray(cv.sample(t)), want, tag + f" host batch({m})")
         done += 1
