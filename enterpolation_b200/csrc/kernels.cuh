@@ -669,6 +669,15 @@ __device__ __forceinline__ void bspline_body(const CurveDev<R>& c, const SampleS
       }
     }
     if (!have_row) valid = bspline_span<R, EQUI>(c, x, index, top);
+    if constexpr (EQUI) {
+      // Equidistant knots with a NEGATIVE step (the builders take domain(a, b) with a > b as it comes): list.rs:476-488
+      // then returns max.min(min_index + 1) BELOW its `min`, and the reference panics on the element access at
+      // `index - degree + i` (bspline/mod.rs:131, usize underflow). Same outcome here, and no gather in front of the tables.
+      if (index < (uint32_t)p) {
+        valid = false;
+        index = (uint32_t)p;
+      }
+    }
     if (!active) continue;
     const uint32_t first = index - (uint32_t)p;
     R kn[2 * P_CAP];

@@ -486,6 +486,9 @@ struct BSpline {
   }
   Output eval(R scalar) const {
     const size_t index = index_of(scalar);
+    // `index - degree + i` underflows when the search returns an index below its lower cut (Equidistant with a negative
+    // step, list.rs:486-487): the element access at bspline/mod.rs:131 is then out of bounds, a panic upstream
+    if (index < degree) throw Panic{};
     auto ws = space.workspace();
     for (size_t i = 0; i <= degree; ++i) ws[i] = elements.eval(index - degree + i);
     for (size_t r = 1; r <= degree; ++r) {

@@ -1051,3 +1051,31 @@ def test_take_f32_generic_stepper_runs(name, builder):
     for n_total, first, count in cases:
         got = curve.take_device(n_total, first, count).cpu().numpy()
         assert_bits_equal(got, ref.take(n_total, first, count, threads=8), f"{name} take({n_total}) [{first}, +{count})")
+
+
+# The builders take `domain(a, b)` with a > b as it comes (no check upstream): the equidistant knots then DESCEND.
+# Open B-splines: list.rs:476-488 returns `max.min(min_index + 1)`, which is below the lower cut for parameters between the
+# first knot and knot[degree]; `index - degree` underflows and the element access panics (bspline/mod.rs:131) -> NaN +
+# invalid counter here (found by the seeded fuzz sweep: the kernel used to gather in front of its tables instead).
+# Parameters beyond the first knot fail `to_usize` (negative quotient); Linear: the same through upper_border.
+@pytest.mark.parametrize("scalar", ["f32", "f64"])
+@pytest.mark.parametrize("kind,degree,dim,weighted", [("open", 1, 1, 0), ("open", 3, 4, 0), ("open", 7, 1, 0), ("open", 9, 2, 1),
+                                                      ("clamped", 3, 3, 1), ("clamped", 5, 2, 0), ("linear", 1, 3, 0)])
+def test_descending_equidistant_knots(scalar, kind, degree, dim, weighted):
+    dtype = DT[scalar]
+    n = degree + 6
+    el = rand_elements(n, dim, dtype, 0xD5C)
+    w = (dtype(0.5) + u01(n, 0xD5D, dtype)).astype(dtype)
+    if kind == "linear":
+        b = Linear.builder()
+        b = b.elements_with_weights(el, w) if weighted else b.elements(el)
+        b = b.equidistant(scalar).domain(2.75, 1.5)
+    else:
+        b = BSpline.builder().open() if kind == "open" else BSpline.builder().clamped()
+        b = b.elements_with_weights(el, w) if weighted else b.elements(el)
+        b = b.equidistant(scalar).degree(degree).domain(2.75, 1.5).dynamic()
+    rng = np.random.default_rng(degree * 10 + dim)
+    t = np.concatenate([rng.uniform(1.0, 3.25, 4000), [2.75, 1.5, np.nextafter(2.75, 3), np.nextafter(2.75, 0)]]).astype(dtype)
+    curve, ref = check_curve(b, t, what=f"descending {kind} degree {degree} {scalar}")
+    want, inv = ref.eval(t, return_invalid=True)
+    assert inv > 0 and np.isfinite(want).any()
