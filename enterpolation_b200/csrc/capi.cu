@@ -676,8 +676,9 @@ constexpr uint64_t GENERIC_RUNS_VALUES = 1ull << 22;  // distinct values per pas
 // repeats its parameter in runs (rows.cuh RUNS), so per binade and per pass of <= 2^22 values the
 // distinct stepper values are generated (stepper_strided_kernel), evaluated ONCE by whatever batch kernel the curve
 // has, and expanded into the output at the store roof (runs_expand_kernel). Scratch comes from the stream-ordered
-// allocator (cudaMallocAsync on the caller's stream). Only for curves without input adaptors over a finite domain: no
-// parameter can make the reference panic, so the invalid counter needs no per-sample accounting.
+// allocator (cudaMallocAsync on the caller's stream). Only for curves without input adaptors whose in-domain
+// parameters cannot make the reference panic (domain_cannot_panic below): the invalid counter then needs no per-sample
+// accounting.
 // The device's default stream-ordered pool returns freed memory to the OS at the next synchronisation unless told to
 // keep some: let it keep the scratch of one pass, so that repeated takes do not re-allocate it every call.
 static void keep_scratch_in_pool(int device) {
@@ -698,6 +699,22 @@ static void keep_scratch_in_pool(int device) {
     }
   }
   cudaGetLastError();
+}
+
+// Can a parameter inside the curve's (finite) domain make the reference panic? Only equidistant knots can
+// (`to_usize().unwrap()`, list.rs:456,486,539-540; a B-spline index below the lower cut, bspline/mod.rs:131), and only
+// degenerate ones: a zero, negative or non-finite step (the builders accept domain(a, a) and domain(a, b) with a > b), or
+// a step so small against the magnitude of the knots that they collapse onto each other. The run paths evaluate VALUES,
+// not samples, so they leave such curves to the per-sample kernels and their counter. Sufficient condition (f32, the
+// only scalar with runs): step >= 2^-20 * max(|offset|, |domain|) keeps the rounding of (x - offset) / step below 1/8
+// for every parameter within a few ulps of the domain, so the quotient stays inside [min - 1/8, len + 1/8].
+static bool domain_cannot_panic(const Resolved& r) {
+  if (!std::isfinite(r.domain[0]) || !std::isfinite(r.domain[1])) return false;
+  if (r.kind == ENTERP_BEZIER || r.knot_base != ENTERP_KNOTS_EQUIDISTANT) return true;
+  const double step = r.eq_step;
+  if (!(step > 0) || !std::isfinite(step) || !std::isfinite(r.eq_offset)) return false;
+  const double m = std::fmax(std::fabs(r.eq_offset), std::fmax(std::fabs(r.domain[0]), std::fabs(r.domain[1])));
+  return step >= 1.17549435e-38 && step >= m * (1.0 / 1048576.0);
 }
 
 enterp_status generic_runs_take(const enterp_curve& cv, const Replica& rp, const SampleSrc<float>& s, void* out, cudaStream_t st) {
@@ -763,7 +780,7 @@ enterp_status dispatch_eval(const enterp_curve& cv, const Replica& rp, const Sam
   const bool equi = r.knot_base != ENTERP_KNOTS_SORTED;
   // a take the generic kernels would evaluate sample by sample although its f32 stepper repeats itself (see above)
   const bool generic_runs = sizeof(R) == 4 && s.t == nullptr && !g_no_generic_runs && cv.pre.empty() && vec_ok &&
-                            std::isfinite(r.domain[0]) && std::isfinite(r.domain[1]) && s.first + s.count >= GENERIC_RUNS_FROM + (1ull << 16) &&
+                            domain_cannot_panic(r) && s.first + s.count >= GENERIC_RUNS_FROM + (1ull << 16) &&
                             s.first + s.count < (1ull << 62);
   auto take_runs = [&]() -> enterp_status {
     if constexpr (sizeof(R) == 4) return generic_runs_take(cv, rp, s, out, st);
@@ -1201,8 +1218,7 @@ enterp_status host_common(enterp_curve* c, const int* devices, int n_devices, bo
     // finite and inside the domain, no sample can make the reference panic, and the per-value batch evaluation
     // leaves the invalid counter where the per-sample take would)
     const Resolved& rr = c->core->r;
-    j.rle = take && !g_no_rle && rr.scalar == ENTERP_F32 && c->pre.empty() && std::isfinite(rr.domain[0]) &&
-            std::isfinite(rr.domain[1]) && n_total > (1ull << (24 + RLE_MIN_SHIFT)) && first + count > (1ull << (24 + RLE_MIN_SHIFT));
+    j.rle = take && !g_no_rle && rr.scalar == ENTERP_F32 && c->pre.empty() && domain_cannot_panic(rr) && n_total > (1ull << (24 + RLE_MIN_SHIFT)) && first + count > (1ull << (24 + RLE_MIN_SHIFT));
     j.hybrid = j.rle && !g_rle_only;
   }
   std::vector<HostLane> lanes((size_t)n_devices);

@@ -495,7 +495,7 @@ void build_tables(const enterp_curve_desc& d, const Shape& s, Resolved& r) {
       if (d.weighted) {
         const R wi = w[i];
         for (int c = 0; c < d.dim; ++c) out[i * r.dh + c] = (wi == R(0)) ? el[i * d.dim + c] : el[i * d.dim + c] * wi;
-        out[i * r.dh + d.dim] = wi;
+        out[i * r.dh + d.dim] = (wi == R(0)) ? R(0) : wi;  // Homogeneous::infinity stores R::zero(): a -0.0 weight loses its sign
       } else {
         for (int c = 0; c < d.dim; ++c) out[i * r.dh + c] = el[i * d.dim + c];
       }

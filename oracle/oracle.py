@@ -15,7 +15,8 @@ import numpy as np
 from . import desc as _abi  # the checker's own view of the descriptor structs: the product package is not imported
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libenterp_oracle.so")
+# ENTERP_ORACLE_SO: another build of the same sources (tests/test_oracle_sanitized.py points it at the ASan/UBSan build)
+_SO = os.environ.get("ENTERP_ORACLE_SO") or os.path.join(_HERE, "libenterp_oracle.so")
 _lib = None
 
 

@@ -7,76 +7,12 @@ import numpy as np
 import pytest
 import torch
 
-from enterpolation_b200 import Bezier, BSpline, Linear, easing as E
 from oracle import oracle
 
-from util import assert_bits_equal, u01
+from fuzzgen import DT, _degenerate_curve, _degenerate_inputs, _random_const_equidistant, _random_curve, _weird
+from util import assert_bits_equal
 
 pytestmark = pytest.mark.gpu
-
-DT = {"f32": np.float32, "f64": np.float64}
-
-
-def _elements(rng, b, n, dim, dtype, weighted):
-    el = (rng.random((n, dim)) * 2 - 1).astype(dtype)
-    el = el if dim > 1 else el[:, 0]
-    if weighted:
-        w = (0.25 + rng.random(n)).astype(dtype)
-        if rng.random() < 0.1:
-            w[rng.integers(0, n)] = 0  # a zero weight is a direction (homogeneous.rs:83-88)
-        return b.elements_with_weights(el, w)
-    return b.elements(el)
-
-
-def _sorted_knots(rng, n, dtype):
-    k = np.cumsum(0.05 + rng.random(n) * rng.choice([1.0, 1.0, 40.0]))
-    if rng.random() < 0.3 and n > 6:
-        for i in rng.integers(1, n - 1, size=max(1, n // 10)):
-            k[i] = k[i - 1]  # repeated knots
-        k = np.sort(k)
-    return (k * rng.choice([1.0, 1e-3, 1e4]) + rng.choice([0.0, -3.0, 1e3])).astype(dtype)
-
-
-def _random_curve(rng):
-    scalar = rng.choice(["f32", "f64"])
-    dtype = DT[scalar]
-    dim = int(rng.integers(1, 5))
-    weighted = bool(rng.random() < 0.25)
-    kind = rng.choice(["linear", "bezier", "bspline"], p=[0.35, 0.15, 0.5])
-    size = int(rng.choice([3, 5, 9, 33, 200, 600, 5000, 9000], p=[0.15, 0.2, 0.2, 0.15, 0.1, 0.08, 0.07, 0.05]))
-    if kind == "linear":
-        n = max(2, size)
-        b = _elements(rng, Linear.builder(), n, dim, dtype, weighted)
-        how = rng.choice(["sorted", "domain", "normalized", "distance"])
-        if how == "sorted":
-            b = b.knots(_sorted_knots(rng, n, dtype))
-        else:
-            b = b.equidistant(scalar)
-            b = {"domain": lambda: b.domain(float(rng.normal()), float(rng.normal()) + 3.5),
-                 "normalized": lambda: b.normalized(),
-                 "distance": lambda: b.distance(float(rng.normal()), float(rng.choice([0.125, 0.1, 3.0, 1e-4])))}[how]()
-        if rng.random() < 0.3:
-            b = b.easing(rng.choice([E.flip, E.smoothstep, E.smootherstep, E.smoothstart(3), E.smoothend(2), E.Plateau(0.35)]))
-    elif kind == "bezier":
-        n = int(rng.choice([1, 2, 3, 4, 6, 8, 9, 16, 17, 30]))
-        b = _elements(rng, Bezier.builder(), n, dim, dtype, weighted)
-        b = b.domain(float(rng.normal()), float(rng.normal()) + 4.0, scalar) if rng.random() < 0.4 else b.normalized(scalar)
-        b = b.constant() if rng.random() < 0.5 else b.dynamic()
-    else:
-        degree = int(rng.choice([1, 2, 3, 3, 3, 4, 5, 7, 8]))
-        n = max(degree + 2, size)
-        mode = rng.choice(["open", "clamped", "legacy"], p=[0.3, 0.5, 0.2])
-        b = BSpline.builder()
-        b = {"open": b.open, "clamped": b.clamped, "legacy": b.legacy}[mode]()
-        b = _elements(rng, b, n, dim, dtype, weighted)
-        if mode == "legacy" or rng.random() < 0.5:
-            nk = {"open": n + degree - 1, "clamped": n - degree + 1, "legacy": n + degree + 1}[mode]
-            b = b.knots(_sorted_knots(rng, nk, dtype))
-        else:
-            b = b.equidistant(scalar).degree(degree)
-            b = b.normalized() if rng.random() < 0.4 else b.domain(float(rng.normal()), float(rng.normal()) + 3.5)
-        b = b.dynamic() if rng.random() < 0.6 else b.constant(degree + 1)
-    return scalar, b
 
 
 def _check(rng, scalar, b, tag):
@@ -130,21 +66,50 @@ def test_random_curves(seed):
         done += 1
 
 
-def _random_const_equidistant(rng):
-    """ConstEquidistant knots (list.rs:566-721): no builder chain reaches them, so _random_curve never does."""
-    scalar = rng.choice(["f32", "f64"])
-    dtype = DT[scalar]
-    dim = int(rng.integers(1, 5))
-    n = int(rng.choice([2, 3, 9, 33, 200, 5000]))
-    el = (rng.random((n, dim)) * 2 - 1).astype(dtype)
-    el = el if dim > 1 else el[:, 0]
-    if rng.random() < 0.5:
-        return scalar, Linear.equidistant_unchecked(el, scalar)
-    degree = int(rng.choice([1, 2, 3, 4, 6]))
-    if n <= degree:
-        return scalar, Linear.equidistant_unchecked(el, scalar)
-    w = (0.25 + rng.random(n)).astype(dtype) if rng.random() < 0.3 else None
-    return scalar, BSpline.new_const_equidistant(el, n + degree - 1, scalar, workspace=None if rng.random() < 0.5 else degree + 1, weights=w)
+@pytest.mark.parametrize("seed", range(_FIRST // 2, _FIRST // 2 + max(1, _COUNT // 2)))
+def test_random_degenerate_curves(seed):
+    from enterpolation_b200.curve import Take
+    rng = np.random.default_rng(0xDE6E + seed)
+    done = 0
+    while done < 10:
+        scalar, b = _degenerate_curve(rng)
+        try:
+            c = b.build()
+        except Exception:
+            continue
+        r = oracle.OracleCurve(b.to_desc())
+        base = c  # the invalid counter lives with the core curve
+        pick = rng.random()
+        if pick < 0.2:
+            c, r = c.clamp(), r.clamp()
+        elif pick < 0.4:  # Slice::new with bounds as they come: empty, reversed, non-finite (adaptors.rs:61-81)
+            d0 = r.domain()
+            a = float(rng.choice([float(d0[0]), 0.0, _weird(rng, DT[scalar]), rng.normal()]))
+            bb = float(rng.choice([a, float(d0[1]), _weird(rng, DT[scalar]), rng.normal()]))
+            c, r = c.slice(a, bb), r.slice(a, bb)
+        d = r.domain()
+        tag = f"seed {seed} case {done}"
+        t = _degenerate_inputs(rng, DT[scalar], float(d[0]), float(d[1]), int(rng.choice([7, 1000, 20011])))
+        want, inv = r.eval(t, return_invalid=True)
+        before = base.invalid_count()
+        got = c.sample_device(torch.from_numpy(t).cuda()).cpu().numpy()
+        assert_bits_equal(got, want, tag + " batch")
+        assert base.invalid_count() - before == inv, tag + " batch invalid count"
+        assert_bits_equal(np.asarray(c.sample(t)), want, tag + " host batch")
+        idx, fac = c.span_device(torch.from_numpy(t).cuda())
+        widx, wfac = r.span(t)
+        assert np.array_equal(idx.cpu().numpy().view(np.uint32), widx), tag + " span indices"
+        assert_bits_equal(fac.cpu().numpy(), wfac, tag + " span factor")
+        n = int(rng.choice([1, 2, 33, 4099, 70001]))
+        total = n + int(rng.choice([0, 12345, (1 << 27) + 5, (1 << 32) + 77]))
+        first = int(rng.integers(0, total - n + 1))
+        want, inv = r.take(total, first, n, return_invalid=True)
+        before = base.invalid_count()
+        got = c.take_device(total, first, n).cpu().numpy()
+        assert_bits_equal(got, want, tag + f" take({total})[{first}:+{n}]")
+        assert base.invalid_count() - before == inv, tag + " take invalid count"
+        assert_bits_equal(Take(c, total, first, n).collect(), want, tag + f" host take({total})[{first}:+{n}]")
+        done += 1
 
 
 # Windows of long takes laid over the indices where an f32 stepper changes its run length (2^24 .. 2^32, rows.cuh RUNS,
@@ -172,10 +137,10 @@ def test_random_windows_over_run_boundaries(seed):
             total = first + n + int(rng.choice([0, 1, 12345, 1 << k]))
             tag = f"seed {seed} case {done} {what} take({total})[{first}:+{n}]"
             want, inv = rv.take(total, first, n, return_invalid=True)
-            before = c.invalid_count()
+            before = base.invalid_count()
             got = cv.take_device(total, first, n).cpu().numpy()
             assert_bits_equal(got, want, tag + " device")
-            assert c.invalid_count() - before == inv, tag + " invalid count"
+            assert base.invalid_count() - before == inv, tag + " invalid count"
             got = Take(cv, total, first, n).collect()
             assert_bits_equal(got, want, tag + " host")
             m = int(rng.choice([1, 1000, 20011]))

@@ -183,6 +183,22 @@ def test_bezier(scalar, n, dim, weighted, domain):
     check_curve(b, t, what=f"bezier {scalar} n{n} d{dim} w{weighted} dom{domain}")
 
 
+def test_negative_zero_weight_becomes_zero():
+    """`weighted_or_infinite` (homogeneous.rs:83-88) sends a weight that `is_zero()` — -0.0 included — to
+    `Homogeneous::infinity`, whose rational is `R::zero()` = +0.0: the sign of the resulting infinities follows the element,
+    not the weight's sign bit (found by the degenerate fuzz sweep: -inf upstream, +inf here)."""
+    for scalar in ("f32", "f64"):
+        dtype = DT[scalar]
+        el = np.array([[-0.93, -0.28], [-0.95, -0.76], [0.72, 0.38]], dtype=dtype)
+        w = np.array([-0.0, 0.78, 0.38], dtype=dtype)
+        t = np.array([-0.0, 0.0, -1e-39, 0.25, 1.0], dtype=dtype)
+        for b in (Linear.builder().elements_with_weights(el, w).equidistant(scalar).normalized(),
+                  Bezier.builder().elements_with_weights(el, w).normalized(scalar).constant(),
+                  BSpline.builder().clamped().elements_with_weights(el, w).equidistant(scalar).degree(2).normalized().dynamic()):
+            curve, ref = check_curve(b, t, take_n=5, what=f"-0.0 weight {type(b).__name__} {scalar}")
+            assert np.all(np.asarray(curve.sample(t[:1])) == -np.inf)
+
+
 def test_weight_zero_is_a_direction():  # homogeneous.rs:83-88; bezier/builder.rs:237-245 ends in inf
     b = Bezier.builder().elements_with_weights([(1.0, 1.0), (2.0, 4.0), (3.0, 0.0)]).normalized("f64").constant()
     check_curve(b, np.linspace(-0.5, 1.5, 201), what="weight zero")
@@ -1079,3 +1095,29 @@ def test_descending_equidistant_knots(scalar, kind, degree, dim, weighted):
     curve, ref = check_curve(b, t, what=f"descending {kind} degree {degree} {scalar}")
     want, inv = ref.eval(t, return_invalid=True)
     assert inv > 0 and np.isfinite(want).any()
+
+
+# The stepper-run paths (generic runs on the device, run-length transfer to host buffers) evaluate distinct VALUES; a
+# curve whose in-domain parameters make the reference panic (zero-width or descending equidistant knots: the quotient is
+# NaN or negative) must keep the per-sample kernels, or the invalid counter counts values instead of samples (found by the
+# degenerate fuzz sweep: take(2^32 + 78)[694938518:+1] counted 2).
+@pytest.mark.parametrize("domain", [(0.0, 0.0), (2.75, 1.5), (1e4, 1e4), ("distance", 0.2992507, 2.9e-39), ("distance", 1e4, 2.0 ** -14)])
+@pytest.mark.parametrize("kind", ["bspline", "linear"])
+def test_run_paths_count_invalid_samples_not_values(domain, kind):
+    from enterpolation_b200.curve import Take
+    el = rand_elements(9, 4, np.float32, 0xBAD)
+    b = BSpline.builder().open().elements(el).equidistant("f32").degree(5) if kind == "bspline" else Linear.builder().elements(el).equidistant("f32")
+    # ("distance", offset, step): knots that collapse onto each other (a step far below the ulp of the offset)
+    b = b.distance(domain[1], domain[2]) if domain[0] == "distance" else b.domain(*domain)
+    if kind == "bspline":
+        b = b.dynamic()
+    curve, ref = b.build(), oracle.OracleCurve(b.to_desc())
+    total = (1 << 32) + 78
+    for first, n in ((694938518, 1), ((1 << 26) - 3000, 70001), ((1 << 31) - 5, 300000)):
+        want, inv = ref.take(total, first, n, return_invalid=True)
+        before = curve.invalid_count()
+        assert_bits_equal(curve.take_device(total, first, n).cpu().numpy(), want, f"{kind} {domain} device take")
+        assert curve.invalid_count() - before == inv, f"{kind} {domain} take({total})[{first}:+{n}] invalid count"
+        before = curve.invalid_count()
+        assert_bits_equal(Take(curve, total, first, n).collect(), want, f"{kind} {domain} host take")
+        assert curve.invalid_count() - before == inv, f"{kind} {domain} host take invalid count"
