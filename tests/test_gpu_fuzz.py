@@ -137,10 +137,10 @@ def test_random_windows_over_run_boundaries(seed):
             total = first + n + int(rng.choice([0, 1, 12345, 1 << k]))
             tag = f"seed {seed} case {done} {what} take({total})[{first}:+{n}]"
             want, inv = rv.take(total, first, n, return_invalid=True)
-            before = base.invalid_count()
+            before = c.invalid_count()
             got = cv.take_device(total, first, n).cpu().numpy()
             assert_bits_equal(got, want, tag + " device")
-            assert base.invalid_count() - before == inv, tag + " invalid count"
+            assert c.invalid_count() - before == inv, tag + " invalid count"
             got = Take(cv, total, first, n).collect()
             assert_bits_equal(got, want, tag + " host")
             m = int(rng.choice([1, 1000, 20011]))
