@@ -24,8 +24,10 @@
  *  - outputs are dense AoS `[n][dim]` of the curve scalar (weighted curves emit the `dim`
  *    projected components, src/weights/homogeneous.rs:134-136);
  *  - where the reference would panic (NaN/inf/negative into `to_usize().unwrap()`,
- *    src/base/list.rs:456,486,539-540) the device writes NaN into every component of that sample
- *    and bumps a per-curve counter readable with enterp_invalid_count();
+ *    src/base/list.rs:456,486,539-540; a B-spline span index below the lower cut — descending or
+ *    collapsed equidistant knots — at the element access of src/bspline/mod.rs:131) the device writes
+ *    NaN into every component of that sample and bumps a per-curve counter readable with
+ *    enterp_invalid_count();
  *  - no CPU fallback exists: every eval entry point returns ENTERP_NO_DEVICE / ENTERP_CUDA_ERROR
  *    when no B200 is usable.
  */
